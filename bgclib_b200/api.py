@@ -1,0 +1,170 @@
+"""Public Python surface: the "Distance calculation" feature BGClib announces
+for BGCCollection (BGClib/Readme.md:16-18; the commented-out ``--comparative``
+switch, BGCtoolkit.py:157-161), computed on B200 through libbgca.so.
+
+    scores = domain_pair_scores(collection)          # all-vs-all Gotoh scores
+    result = bgc_similarity(collection)              # BGC x BGC similarity
+    attach()                                         # optional: adds both as methods
+                                                     # of the reference's BGCCollection
+
+Defaults (this build's choice where the reference defines nothing; SURVEY.md
+App. C/D): BLOSUM62, open -12, extend -1 (Biopython's blastp preset; a gap of
+length k scores open + (k-1)*extend), mode "local", CBP proteins only.
+
+Multi-GPU: run one process per GPU under torchrun.  When torch.distributed is
+initialised, every rank scores its share of the tile list and the partial
+results are combined with ONE NCCL all-reduce(max) at the end; every rank
+returns the full result.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+
+from .engine import Engine, MODE_LOCAL, resolve_mode
+from .extract import DomainBatch, DomainRecord, extract
+
+_ENGINES = {}
+
+INT32_MIN = int(np.iinfo(np.int32).min)
+
+
+def get_engine(device: Optional[int] = None) -> Engine:
+    import torch
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    device = int(device)
+    if device not in _ENGINES:
+        _ENGINES[device] = Engine(device)
+    return _ENGINES[device]
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist, dist.get_rank(), dist.get_world_size()
+    return None, 0, 1
+
+
+@dataclass
+class DomainPairScores:
+    scores: np.ndarray              # int32 [n, n], symmetric, diagonal = self scores
+    index: List[DomainRecord]       # row/column identity
+    computed: Optional[np.ndarray]  # bool [n, n] when same_type_only masked some pairs, else None
+    plan: dict                      # tile-plan statistics of this rank
+
+
+@dataclass
+class BGCSimilarity:
+    sim: np.ndarray                 # float64 [B, B]
+    best: np.ndarray                # int64   [B, B]
+    self_score: np.ndarray          # int64   [B]
+    bgc_ids: List[str]
+    index: List[DomainRecord]
+    plan: dict
+
+
+def _as_batch(source, unit, cbp_only, alias, domain_types) -> DomainBatch:
+    if isinstance(source, DomainBatch):
+        return source
+    return extract(source, unit=unit, cbp_only=cbp_only, alias=alias, domain_types=domain_types)
+
+
+def domain_pair_scores(source, *, mode="local", matrix="BLOSUM62", open_gap_score=-12,
+                       extend_gap_score=-1, unit="domain", cbp_only=True, alias=None,
+                       domain_types=None, same_type_only=False, device=None,
+                       return_device=False) -> DomainPairScores:
+    """All-vs-all affine-gap alignment scores of the domain sequences in ``source``.
+
+    Raises ValueError for an empty selection, a zero-length sequence or a letter
+    outside ``ARNDCQEGHILKMFPSTWYVBZX*`` (as Biopython's PairwiseAligner would).
+    Pairs skipped by ``same_type_only`` hold 0 (local) / INT32_MIN (global) and
+    are flagged False in ``computed``.
+    """
+    batch = _as_batch(source, unit, cbp_only, alias, domain_types)
+    n = len(batch)
+    if n == 0:
+        raise ValueError("no domain sequences selected")
+    eng = get_engine(device)
+    eng.set_scoring(matrix, open_gap_score, extend_gap_score, mode)
+    torch = eng.torch
+    dist, rank, world = _dist()
+    eng.pack(batch.sequences, type_of_seq=batch.type_of_seq if same_type_only else None)
+    plan = eng.plan(same_type_only=same_type_only, rank=rank, world=world)
+    scores = torch.full((n, n), INT32_MIN, dtype=torch.int32, device=eng.tdev)
+    eng.score(scores=scores)
+    if dist is not None:
+        dist.all_reduce(scores, op=dist.ReduceOp.MAX)
+    computed = None
+    if same_type_only:
+        computed = scores != INT32_MIN
+        if resolve_mode(mode) == MODE_LOCAL:
+            scores = torch.where(computed, scores, torch.zeros_like(scores))
+    if return_device:
+        return DomainPairScores(scores, batch.records, computed, plan)
+    return DomainPairScores(scores.cpu().numpy(), batch.records,
+                            None if computed is None else computed.cpu().numpy(), plan)
+
+
+def bgc_similarity(source, *, matrix="BLOSUM62", open_gap_score=-12, extend_gap_score=-1,
+                   unit="domain", cbp_only=True, alias=None, domain_types=None, same_type_only=True,
+                   bgc_ids=None, device=None, return_device=False) -> BGCSimilarity:
+    """BGC x BGC similarity from local domain-pair scores:
+
+        rowbest[d,b] = max{ s(d,e) : e in b, type(e) == type(d) }      (0 if none)
+        best[a,b]    = sum_{d in a} rowbest[d,b]
+        self[a]      = sum_{d in a} s(d,d)
+        sim[a,b]     = (best[a,b] + best[b,a]) / (self[a] + self[b])    (0/0 -> 0, sim[a,a] = 1)
+
+    The domain-pair matrix is never materialised: the DP kernels' epilogue does the
+    segmented max (atomicMax into rowbest), a second kernel the segmented sums.
+    ``bgc_ids`` fixes the row order (ids absent from ``source`` get zero rows).
+    """
+    batch = _as_batch(source, unit, cbp_only, alias, domain_types)
+    ids = list(batch.bgc_ids)
+    bgc_of = batch.bgc_of_seq
+    if bgc_ids is not None:
+        pos = {b: i for i, b in enumerate(bgc_ids)}
+        missing = [b for b in ids if b not in pos]
+        if missing:
+            raise ValueError(f"bgc_ids lacks BGCs present in source: {missing[:3]}")
+        remap = np.asarray([pos[b] for b in ids], dtype=np.int32)
+        bgc_of = remap[bgc_of] if len(bgc_of) else bgc_of
+        ids = list(bgc_ids)
+    B = len(ids)
+    n = len(batch)
+    if B == 0:
+        raise ValueError("no BGCs selected")
+    eng = get_engine(device)
+    torch = eng.torch
+    if n == 0:
+        z = np.zeros((B, B))
+        return BGCSimilarity(z, z.astype(np.int64), np.zeros(B, np.int64), ids, [], {})
+    eng.set_scoring(matrix, open_gap_score, extend_gap_score, "local")
+    dist, rank, world = _dist()
+    eng.pack(batch.sequences, type_of_seq=batch.type_of_seq, bgc_of_seq=bgc_of, n_bgc=B)
+    plan = eng.plan(same_type_only=same_type_only, rank=rank, world=world)
+    rowbest = torch.zeros((n, B), dtype=torch.int32, device=eng.tdev)
+    selfsc = torch.zeros((n,), dtype=torch.int32, device=eng.tdev)
+    eng.score(rowbest=rowbest, selfsc=selfsc, type_check=False)
+    if dist is not None:
+        dist.all_reduce(rowbest, op=dist.ReduceOp.MAX)
+        dist.all_reduce(selfsc, op=dist.ReduceOp.MAX)
+    sim, best, selfsum = eng.reduce_bgc(rowbest, selfsc)
+    if return_device:
+        return BGCSimilarity(sim, best, selfsum, ids, batch.records, plan)
+    return BGCSimilarity(sim.cpu().numpy(), best.cpu().numpy(), selfsum.cpu().numpy(), ids,
+                         batch.records, plan)
+
+
+def attach(collection_cls=None):
+    """Adds ``domain_pair_scores`` / ``similarity_matrix`` as methods of the
+    reference's BGCCollection (BGClib/BGClib.py:750) — state is NOT stored on
+    the instances, so they stay picklable (BGCtoolkit.py:1249)."""
+    if collection_cls is None:
+        from BGClib import BGCCollection as collection_cls   # the real reference, if importable
+    collection_cls.domain_pair_scores = lambda self, **kw: domain_pair_scores(self, **kw)
+    collection_cls.similarity_matrix = lambda self, **kw: bgc_similarity(self, **kw)
+    return collection_cls

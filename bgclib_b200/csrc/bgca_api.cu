@@ -1,0 +1,663 @@
+// C ABI of the BGC aligner engine (include/bgca.h): engine lifetime, packer
+// driver, tile planner (K6) and kernel dispatch.  Host code; the kernels live in
+// gotoh_pair16.cuh / gotoh_s32.cuh / pack_reduce.cu.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <queue>
+#include <string>
+#include <vector>
+
+#include "launchers.h"
+#include "variants.h"
+
+using namespace bgca;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess)                                                               \
+            return fail(BGCA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+struct VariantDesc { int G, K; };
+const VariantDesc kVariants[] = {
+#define X(G, K) {G, K},
+    BGCA_VARIANTS(X)
+#undef X
+};
+constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+constexpr int kMaxPackedRows = 32 * 32;   // largest G*K
+
+// Relative issue cost of sweeping one subject of length ~Lq with variant (G,K):
+// (steps) x (instructions per step) x (share of the warp one alignment uses).
+double variant_cost(int G, int K, int Lq)
+{
+    return (double)(Lq + G - 1) * (5.5 * K + 14.0) * (double)G;
+}
+
+// BGCA_FORCE_G=8|16|32 restricts the planner to one group width (tuning aid).
+int forced_group_width()
+{
+    const char *s = std::getenv("BGCA_FORCE_G");
+    return s ? std::atoi(s) : 0;
+}
+
+int pick_variant(int Lq)
+{
+    int best = 0;
+    double best_cost = 0.0;
+    const int force_g = forced_group_width();
+    for (int v = 0; v < kNumVariants; ++v) {
+        const int G = kVariants[v].G, K = kVariants[v].K;
+        if (G * K < Lq) continue;
+        if (force_g && G != force_g && force_g * 32 >= Lq) continue;
+        const double c = variant_cost(G, K, Lq);
+        if (!best || c < best_cost) {
+            best = BGCA_VARIANT_ID(G, K);
+            best_cost = c;
+        }
+    }
+    return best;   // 0: no packed variant covers Lq
+}
+
+// int16 safety of one tile: local scores are bounded by max_sub * min(len),
+// global intermediates by the all-gap path.
+bool fits_int16(int mode, int max_abs_sub, int open, int extend, int Lq, int Ls_max)
+{
+    const long long hi = (long long)max_abs_sub * std::min(Lq, Ls_max);
+    if (hi > 30000) return false;
+    if (mode == BGCA_MODE_GLOBAL) {
+        const long long lo = 3LL * -open + (long long)(-extend) * (Lq + Ls_max + 2) +
+                             (long long)max_abs_sub;   // magnitude of the most negative cell
+        if (lo > 29000) return false;
+    }
+    return true;
+}
+
+struct PlanResult {
+    std::vector<bgca_tile> tiles;   // this rank's tiles, grouped by variant, heavy first
+    bgca_plan_info info{};
+};
+
+// K6 — tile scheduler.  See bgca.h.  All indices are SORTED-space.
+PlanResult make_plan(const int32_t *len, const int32_t *type, int32_t n, int same_type_only, int mode,
+                     int max_abs_sub, int open, int extend, int rank, int world)
+{
+    PlanResult R;
+    std::vector<int64_t> pre(n + 1, 0);
+    for (int i = 0; i < n; ++i) pre[i + 1] = pre[i] + len[i];
+
+    std::vector<bgca_tile> all;
+    int tb = 0;
+    while (tb < n) {
+        int te = n;
+        if (same_type_only && type) {
+            te = tb + 1;
+            while (te < n && type[te] == type[tb]) ++te;
+        }
+        for (int qa = tb; qa < te; qa += 2) {
+            const int qb = (qa + 1 < te) ? qa + 1 : -1;
+            const int La = len[qa], Lb = (qb >= 0) ? len[qb] : 0;
+            const int Lq = std::max(La, Lb);
+            int variant = pick_variant(Lq);
+            const int G = variant >> 8;
+            const int S = te - qa;
+            // subjects per tile: ~16 per alignment group of the CTA, split evenly
+            const int s_max = variant ? (CTA_THREADS / G) * 16 : 256;
+            const int nchunks = (S + s_max - 1) / s_max;
+            const int chunk = (S + nchunks - 1) / nchunks;
+            for (int s0 = qa; s0 < te; s0 += chunk) {
+                const int s1 = std::min(te, s0 + chunk);
+                bgca_tile T{};
+                T.qa = qa; T.qb = qb; T.s_begin = s0; T.s_end = s1;
+                T.variant = variant;
+                if (variant && !fits_int16(mode, max_abs_sub, open, extend, Lq, len[s1 - 1])) T.variant = 0;
+                T.cells = (int64_t)(La + Lb) * (pre[s1] - pre[s0]);
+                all.push_back(T);
+            }
+        }
+        tb = te;
+    }
+
+    // exact accounting of unique pairs (i<=j) per tile
+    auto tile_pairs = [&](const bgca_tile &T, int64_t &pairs, int64_t &cells) {
+        const int64_t sumL = pre[T.s_end] - pre[T.s_begin];
+        pairs = T.s_end - T.s_begin;
+        cells = (int64_t)len[T.qa] * sumL;
+        if (T.qb >= 0) {
+            int64_t p2 = T.s_end - T.s_begin, sl2 = sumL;
+            if (T.s_begin <= T.qa && T.qa < T.s_end) { p2 -= 1; sl2 -= len[T.qa]; }   // (qb, qa) mirrored
+            pairs += p2;
+            cells += (int64_t)len[T.qb] * sl2;
+        }
+    };
+
+    // LPT assignment over the exact cell counts
+    std::vector<int> idx(all.size());
+    std::iota(idx.begin(), idx.end(), 0);
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return all[a].cells > all[b].cells; });
+    using Load = std::pair<int64_t, int>;
+    std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+    for (int r = 0; r < world; ++r) heap.push({0, r});
+    std::vector<int> owner(all.size(), 0);
+    for (int i : idx) {
+        Load l = heap.top();
+        heap.pop();
+        owner[i] = l.second;
+        l.first += all[i].cells;
+        heap.push(l);
+    }
+
+    for (size_t i = 0; i < all.size(); ++i) {
+        int64_t pr, ce;
+        tile_pairs(all[i], pr, ce);
+        R.info.total_pairs += pr;
+        R.info.total_cells += ce;
+        if (owner[i] != rank) continue;
+        R.info.n_pairs += pr;
+        R.info.cells += ce;
+        R.info.cells_computed += all[i].cells;
+        if (all[i].variant == 0) R.info.n_fallback32++;
+        R.tiles.push_back(all[i]);
+    }
+    std::stable_sort(R.tiles.begin(), R.tiles.end(), [](const bgca_tile &a, const bgca_tile &b) {
+        if (a.variant != b.variant) return a.variant > b.variant;
+        return a.cells > b.cells;
+    });
+    R.info.n_tiles = (int64_t)R.tiles.size();
+    int nv = 0, last = -1;
+    for (const auto &T : R.tiles)
+        if (T.variant != last) { ++nv; last = T.variant; }
+    R.info.n_variants = nv;
+    return R;
+}
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t count)
+    {
+        if (count <= cap && p) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) cap = count;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct bgca_engine {
+    int device = 0;
+    int n_sm = 0;
+    // scoring
+    int8_t sub[NSYM * NSYM];
+    int open = -12, extend = -1, mode = BGCA_MODE_LOCAL, max_abs_sub = 11;
+    bool scoring_set = false;
+    // packed batch (host mirrors, SORTED space unless named *_orig)
+    int32_t n = 0, n_bgc = 0;
+    std::vector<int32_t> len, type, bgc, order, inv_order;
+    std::vector<uint32_t> seq_off;
+    std::vector<int32_t> bgc_start, bgc_doms;   // CSR over ORIGINAL indices
+    int64_t packed_bytes = 0;
+    bool packed = false, has_type = false, has_bgc = false;
+    // device buffers
+    DevBuf<uint8_t> d_ascii, d_codes;
+    DevBuf<int64_t> d_offsets_orig;
+    DevBuf<int32_t> d_order, d_len, d_type, d_bgc, d_bgc_start, d_bgc_doms, d_counters, d_pq, d_ps;
+    DevBuf<uint32_t> d_seq_off;
+    DevBuf<unsigned long long> d_err;
+    DevBuf<bgca_tile> d_tiles;
+    DevBuf<int2> d_scratch;
+    // plan
+    std::vector<bgca_tile> tiles;
+    bgca_plan_info plan_info{};
+    bool planned = false;
+    // stats
+    int last_launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+};
+
+extern "C" {
+
+int bgca_version(void) { return BGCA_VERSION; }
+
+const char *bgca_last_error(void) { return g_last_error.c_str(); }
+
+int bgca_create(int device, bgca_engine **out)
+{
+    if (!out) return fail(BGCA_ERR_INVALID, "bgca_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(BGCA_ERR_CUDA, std::string("bgca_create: no usable CUDA device (") +
+                                       cudaGetErrorString(e) + "); this engine has no CPU fallback");
+    if (device < 0 || device >= count) return fail(BGCA_ERR_INVALID, "bgca_create: bad device index");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(BGCA_ERR_CUDA, "bgca_create: device is not sm_100 (B200) class");
+    bgca_engine *E = new bgca_engine();
+    E->device = device;
+    E->n_sm = prop.multiProcessorCount;
+    CUDA_TRY(cudaEventCreate(&E->ev0));
+    CUDA_TRY(cudaEventCreate(&E->ev1));
+    *out = E;
+    return BGCA_OK;
+}
+
+int bgca_destroy(bgca_engine *e)
+{
+    if (!e) return BGCA_OK;
+    cudaSetDevice(e->device);
+    e->d_ascii.release(); e->d_codes.release(); e->d_offsets_orig.release(); e->d_order.release();
+    e->d_len.release(); e->d_type.release(); e->d_bgc.release(); e->d_bgc_start.release();
+    e->d_bgc_doms.release(); e->d_counters.release(); e->d_pq.release(); e->d_ps.release();
+    e->d_seq_off.release(); e->d_err.release(); e->d_tiles.release(); e->d_scratch.release();
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    delete e;
+    return BGCA_OK;
+}
+
+int bgca_set_scoring(bgca_engine *e, const int8_t *sub, int32_t open, int32_t extend, int32_t mode)
+{
+    if (!e || !sub) return fail(BGCA_ERR_INVALID, "bgca_set_scoring: NULL argument");
+    if (mode != BGCA_MODE_LOCAL && mode != BGCA_MODE_GLOBAL)
+        return fail(BGCA_ERR_INVALID, "bgca_set_scoring: mode must be 0 (local) or 1 (global)");
+    if (open > 0 || extend > 0 || open > extend)
+        return fail(BGCA_ERR_INVALID, "bgca_set_scoring: need open <= extend <= 0 (Gotoh H/E/F form)");
+    if (open < -1000 || extend < -1000) return fail(BGCA_ERR_RANGE, "bgca_set_scoring: gap score too large");
+    int mx = 0;
+    for (int i = 0; i < NSYM; ++i)
+        for (int j = 0; j < NSYM; ++j) {
+            if (sub[i * NSYM + j] != sub[j * NSYM + i])
+                return fail(BGCA_ERR_INVALID, "bgca_set_scoring: substitution matrix must be symmetric");
+            mx = std::max(mx, std::abs((int)sub[i * NSYM + j]));
+        }
+    std::memcpy(e->sub, sub, NSYM * NSYM);
+    e->open = open; e->extend = extend; e->mode = mode; e->max_abs_sub = std::max(mx, 1);
+    e->scoring_set = true;
+    e->planned = false;
+    return BGCA_OK;
+}
+
+int bgca_pack(bgca_engine *e, const uint8_t *ascii, const int64_t *offsets, int32_t n,
+              const int32_t *type_of_seq, const int32_t *bgc_of_seq, int32_t n_bgc,
+              int32_t ascii_on_device, void *stream)
+{
+    if (!e || !ascii || !offsets) return fail(BGCA_ERR_INVALID, "bgca_pack: NULL argument");
+    if (n <= 0) return fail(BGCA_ERR_INVALID, "bgca_pack: need at least one sequence");
+    if (bgc_of_seq && (n_bgc <= 0 || n_bgc > 65535))
+        return fail(BGCA_ERR_RANGE, "bgca_pack: n_bgc must be in 1..65535");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(e->device));
+    e->packed = false;
+    e->planned = false;
+
+    std::vector<int32_t> len_orig(n);
+    for (int i = 0; i < n; ++i) {
+        const int64_t l = offsets[i + 1] - offsets[i];
+        if (l < 0) return fail(BGCA_ERR_INVALID, "bgca_pack: offsets must be non-decreasing");
+        if (l == 0) return fail(BGCA_ERR_EMPTY, "sequence " + std::to_string(i) + " has zero length");
+        if (l > 65535) return fail(BGCA_ERR_RANGE, "sequence " + std::to_string(i) + " longer than 65535");
+        len_orig[i] = (int32_t)l;
+    }
+    if (bgc_of_seq)
+        for (int i = 0; i < n; ++i)
+            if (bgc_of_seq[i] < 0 || bgc_of_seq[i] >= n_bgc)
+                return fail(BGCA_ERR_INVALID, "bgca_pack: bgc_of_seq out of range");
+
+    // sort by (type, length, original index)
+    e->order.resize(n);
+    std::iota(e->order.begin(), e->order.end(), 0);
+    std::stable_sort(e->order.begin(), e->order.end(), [&](int a, int b) {
+        const int ta = type_of_seq ? type_of_seq[a] : 0, tb = type_of_seq ? type_of_seq[b] : 0;
+        if (ta != tb) return ta < tb;
+        return len_orig[a] < len_orig[b];
+    });
+    e->n = n;
+    e->n_bgc = bgc_of_seq ? n_bgc : 0;
+    e->has_type = type_of_seq != nullptr;
+    e->has_bgc = bgc_of_seq != nullptr;
+    e->len.resize(n); e->type.assign(n, 0); e->bgc.assign(n, 0); e->seq_off.resize(n);
+    e->inv_order.resize(n);
+    uint64_t off = 0;
+    for (int r = 0; r < n; ++r) {
+        const int o = e->order[r];
+        e->inv_order[o] = r;
+        e->len[r] = len_orig[o];
+        if (type_of_seq) e->type[r] = type_of_seq[o];
+        if (bgc_of_seq) e->bgc[r] = bgc_of_seq[o];
+        e->seq_off[r] = (uint32_t)off;
+        off += (uint64_t)((len_orig[o] + 15) & ~15);
+        if (off > 0xFFFFFFF0ull) return fail(BGCA_ERR_RANGE, "bgca_pack: packed batch exceeds 4 GiB");
+    }
+    e->packed_bytes = (int64_t)off;
+
+    // CSR of domains per BGC, ORIGINAL indices
+    e->bgc_start.assign((size_t)e->n_bgc + 1, 0);
+    e->bgc_doms.assign(bgc_of_seq ? n : 0, 0);
+    if (bgc_of_seq) {
+        for (int i = 0; i < n; ++i) e->bgc_start[bgc_of_seq[i] + 1]++;
+        for (int b = 0; b < n_bgc; ++b) e->bgc_start[b + 1] += e->bgc_start[b];
+        std::vector<int32_t> cur(e->bgc_start.begin(), e->bgc_start.end() - 1);
+        for (int i = 0; i < n; ++i) e->bgc_doms[cur[bgc_of_seq[i]]++] = i;
+    }
+
+    const int64_t total_ascii = offsets[n] - offsets[0];
+    const uint8_t *d_src = ascii + offsets[0];
+    if (!ascii_on_device) {
+        CUDA_TRY(e->d_ascii.reserve((size_t)total_ascii));
+        CUDA_TRY(cudaMemcpyAsync(e->d_ascii.p, ascii + offsets[0], (size_t)total_ascii,
+                                 cudaMemcpyHostToDevice, st));
+        d_src = e->d_ascii.p;
+    }
+    std::vector<int64_t> off_rel(n + 1);
+    for (int i = 0; i <= n; ++i) off_rel[i] = offsets[i] - offsets[0];
+    CUDA_TRY(e->d_offsets_orig.reserve(n + 1));
+    CUDA_TRY(e->d_order.reserve(n));
+    CUDA_TRY(e->d_len.reserve(n));
+    CUDA_TRY(e->d_type.reserve(n));
+    CUDA_TRY(e->d_bgc.reserve(n));
+    CUDA_TRY(e->d_seq_off.reserve(n));
+    CUDA_TRY(e->d_codes.reserve((size_t)off + 16));
+    CUDA_TRY(e->d_err.reserve(1));
+    CUDA_TRY(e->d_bgc_start.reserve(e->bgc_start.size()));
+    CUDA_TRY(e->d_bgc_doms.reserve(std::max<size_t>(e->bgc_doms.size(), 1)));
+    CUDA_TRY(cudaMemcpyAsync(e->d_offsets_orig.p, off_rel.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->d_order.p, e->order.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->d_len.p, e->len.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->d_type.p, e->type.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->d_bgc.p, e->bgc.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->d_seq_off.p, e->seq_off.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->d_bgc_start.p, e->bgc_start.data(), sizeof(int32_t) * e->bgc_start.size(), cudaMemcpyHostToDevice, st));
+    if (!e->bgc_doms.empty())
+        CUDA_TRY(cudaMemcpyAsync(e->d_bgc_doms.p, e->bgc_doms.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(e->d_err.p, 0xFF, sizeof(unsigned long long), st));
+    CUDA_TRY(launch_pack(d_src, e->d_offsets_orig.p, e->d_order.p, e->d_seq_off.p, e->d_len.p, n,
+                         e->d_codes.p, e->d_err.p, st));
+    unsigned long long err = 0;
+    CUDA_TRY(cudaMemcpyAsync(&err, e->d_err.p, sizeof(err), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (err != ~0ULL) {
+        const unsigned seq = (unsigned)(err >> 32), pos = (unsigned)(err & 0xFFFFFFFFu);
+        return fail(BGCA_ERR_ALPHABET, "sequence " + std::to_string(seq) + " contains a letter not in the "
+                                       "alphabet ARNDCQEGHILKMFPSTWYVBZX* at position " + std::to_string(pos));
+    }
+    e->packed = true;
+    return BGCA_OK;
+}
+
+int64_t bgca_packed_bytes(const bgca_engine *e) { return (e && e->packed) ? e->packed_bytes : 0; }
+
+int bgca_get_packed(const bgca_engine *e, uint8_t *codes_out, int64_t *offsets_sorted_out,
+                    int32_t *order_out, void *stream)
+{
+    if (!e || !e->packed) return fail(BGCA_ERR_INVALID, "bgca_get_packed: nothing packed");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(e->device));
+    if (codes_out) {
+        CUDA_TRY(cudaMemcpyAsync(codes_out, e->d_codes.p, (size_t)e->packed_bytes, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    if (offsets_sorted_out) {
+        for (int r = 0; r < e->n; ++r) offsets_sorted_out[r] = e->seq_off[r];
+        offsets_sorted_out[e->n] = e->packed_bytes;
+    }
+    if (order_out) std::memcpy(order_out, e->order.data(), sizeof(int32_t) * e->n);
+    return BGCA_OK;
+}
+
+int bgca_plan_host(const int32_t *len_sorted, const int32_t *type_sorted, int32_t n,
+                   int32_t same_type_only, int32_t mode, int32_t max_abs_sub, int32_t open,
+                   int32_t extend, int32_t rank, int32_t world, bgca_tile *tiles_out,
+                   int64_t capacity, int64_t *n_tiles_out, bgca_plan_info *info)
+{
+    if (!len_sorted || n <= 0 || world <= 0 || rank < 0 || rank >= world)
+        return fail(BGCA_ERR_INVALID, "bgca_plan_host: bad arguments");
+    PlanResult R = make_plan(len_sorted, type_sorted, n, same_type_only, mode, max_abs_sub, open, extend,
+                             rank, world);
+    if (n_tiles_out) *n_tiles_out = (int64_t)R.tiles.size();
+    if (info) *info = R.info;
+    if (tiles_out) {
+        const int64_t m = std::min<int64_t>(capacity, (int64_t)R.tiles.size());
+        std::memcpy(tiles_out, R.tiles.data(), sizeof(bgca_tile) * (size_t)m);
+    }
+    return BGCA_OK;
+}
+
+int bgca_plan(bgca_engine *e, int32_t same_type_only, int32_t rank, int32_t world, bgca_plan_info *info)
+{
+    if (!e || !e->packed) return fail(BGCA_ERR_INVALID, "bgca_plan: call bgca_pack first");
+    if (!e->scoring_set) return fail(BGCA_ERR_INVALID, "bgca_plan: call bgca_set_scoring first");
+    if (world <= 0 || rank < 0 || rank >= world) return fail(BGCA_ERR_INVALID, "bgca_plan: bad rank/world");
+    if (same_type_only && !e->has_type)
+        return fail(BGCA_ERR_INVALID, "bgca_plan: same_type_only needs type_of_seq at pack time");
+    CUDA_TRY(cudaSetDevice(e->device));
+    PlanResult R = make_plan(e->len.data(), e->has_type ? e->type.data() : nullptr, e->n, same_type_only,
+                             e->mode, e->max_abs_sub, e->open, e->extend, rank, world);
+    e->tiles.swap(R.tiles);
+    e->plan_info = R.info;
+    CUDA_TRY(e->d_tiles.reserve(e->tiles.size()));
+    if (!e->tiles.empty())
+        CUDA_TRY(cudaMemcpy(e->d_tiles.p, e->tiles.data(), sizeof(bgca_tile) * e->tiles.size(),
+                            cudaMemcpyHostToDevice));
+    e->planned = true;
+    if (info) *info = e->plan_info;
+    return BGCA_OK;
+}
+
+static void fill_params(const bgca_engine *e, ScoreParams &p, int32_t *scores, int32_t *rowbest,
+                        int32_t *selfsc, int type_check)
+{
+    std::memset(&p, 0, sizeof(p));
+    p.codes = e->d_codes.p;
+    p.seq_off = e->d_seq_off.p;
+    p.seq_len = e->d_len.p;
+    p.order = e->d_order.p;
+    p.type_of = e->d_type.p;
+    p.bgc_of = e->d_bgc.p;
+    p.scores = scores;
+    p.rowbest = rowbest;
+    p.selfsc = selfsc;
+    p.n = e->n;
+    p.n_bgc = e->n_bgc;
+    p.open = e->open;
+    p.extend = e->extend;
+    p.type_check = type_check;
+    std::memcpy(p.sub, e->sub, NSYM * NSYM);
+}
+
+static int run_s32_pairs(bgca_engine *e, ScoreParams &p, const int32_t *d_pq, const int32_t *d_ps,
+                         long long npairs, int32_t *out_list, cudaStream_t st)
+{
+    int max_len = 0;
+    for (int r = 0; r < e->n; ++r) max_len = std::max(max_len, e->len[r]);
+    int grid = e->n_sm * 4;
+    const long long warps_needed = (npairs + 0);
+    if ((long long)grid * (CTA_THREADS / 32) > warps_needed)
+        grid = (int)std::max<long long>(1, (warps_needed + CTA_THREADS / 32 - 1) / (CTA_THREADS / 32));
+    const int stride = (max_len + 3) & ~3;
+    CUDA_TRY(e->d_scratch.reserve((size_t)grid * (CTA_THREADS / 32) * stride));
+    CUDA_TRY(launch_s32(e->mode, p, d_pq, d_ps, npairs, e->d_scratch.p, stride, out_list, grid, st));
+    e->last_launches++;
+    return BGCA_OK;
+}
+
+int bgca_score(bgca_engine *e, int32_t *scores, int32_t *rowbest, int32_t *selfsc, int32_t type_check,
+               void *stream)
+{
+    if (!e || !e->planned) return fail(BGCA_ERR_INVALID, "bgca_score: call bgca_plan first");
+    if (rowbest && !e->has_bgc) return fail(BGCA_ERR_INVALID, "bgca_score: rowbest needs bgc_of_seq at pack time");
+    if (rowbest && type_check && !e->has_type)
+        return fail(BGCA_ERR_INVALID, "bgca_score: type_check needs type_of_seq at pack time");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(e->device));
+    e->last_launches = 0;
+    ScoreParams p;
+    fill_params(e, p, scores, rowbest, selfsc, type_check);
+
+    // one launch per kernel variant present in the plan (tiles are grouped by variant)
+    std::vector<std::pair<size_t, size_t>> runs;   // [begin, end) per variant
+    for (size_t i = 0; i < e->tiles.size();) {
+        size_t j = i;
+        while (j < e->tiles.size() && e->tiles[j].variant == e->tiles[i].variant) ++j;
+        runs.push_back({i, j});
+        i = j;
+    }
+    CUDA_TRY(e->d_counters.reserve(runs.size() + 1));
+    CUDA_TRY(cudaMemsetAsync(e->d_counters.p, 0, sizeof(int32_t) * (runs.size() + 1), st));
+    CUDA_TRY(cudaEventRecord(e->ev0, st));
+    for (size_t r = 0; r < runs.size(); ++r) {
+        const size_t b = runs[r].first, en = runs[r].second;
+        const int variant = e->tiles[b].variant;
+        if (variant == 0) {
+            // 32-bit fallback: expand the tiles into an explicit (q, s) list
+            std::vector<int32_t> pq, ps;
+            for (size_t i = b; i < en; ++i) {
+                const bgca_tile &T = e->tiles[i];
+                for (int s = T.s_begin; s < T.s_end; ++s) {
+                    pq.push_back(T.qa); ps.push_back(s);
+                    if (T.qb >= 0 && s >= T.qb) { pq.push_back(T.qb); ps.push_back(s); }
+                }
+            }
+            CUDA_TRY(e->d_pq.reserve(pq.size()));
+            CUDA_TRY(e->d_ps.reserve(ps.size()));
+            CUDA_TRY(cudaMemcpyAsync(e->d_pq.p, pq.data(), sizeof(int32_t) * pq.size(), cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(e->d_ps.p, ps.data(), sizeof(int32_t) * ps.size(), cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaStreamSynchronize(st));   // pq/ps are stack-owned host vectors
+            int rc = run_s32_pairs(e, p, e->d_pq.p, e->d_ps.p, (long long)pq.size(), nullptr, st);
+            if (rc != BGCA_OK) return rc;
+            continue;
+        }
+        p.tiles = e->d_tiles.p + b;
+        p.n_tiles = (int32_t)(en - b);
+        p.tile_counter = e->d_counters.p + r;
+        const int G = variant >> 8, K = variant & 0xFF;
+        cudaError_t err = cudaErrorInvalidValue;
+        int grid = 0;
+        const bool local = e->mode == BGCA_MODE_LOCAL;
+        if (G == 8) err = local ? launch_pair16_g8_m0(K, p, e->n_sm, st, &grid) : launch_pair16_g8_m1(K, p, e->n_sm, st, &grid);
+        else if (G == 16) err = local ? launch_pair16_g16_m0(K, p, e->n_sm, st, &grid) : launch_pair16_g16_m1(K, p, e->n_sm, st, &grid);
+        else if (G == 32) err = local ? launch_pair16_g32_m0(K, p, e->n_sm, st, &grid) : launch_pair16_g32_m1(K, p, e->n_sm, st, &grid);
+        if (err != cudaSuccess)
+            return fail(BGCA_ERR_CUDA, std::string("DP kernel launch (G=") + std::to_string(G) + ",K=" +
+                                           std::to_string(K) + "): " + cudaGetErrorString(err));
+        e->last_launches++;
+    }
+    CUDA_TRY(cudaEventRecord(e->ev1, st));
+    e->timed = true;
+    return BGCA_OK;
+}
+
+int bgca_score_pairs32(bgca_engine *e, const int32_t *pi, const int32_t *pj, int64_t npairs,
+                       int32_t *out, void *stream)
+{
+    if (!e || !e->packed || !e->scoring_set) return fail(BGCA_ERR_INVALID, "bgca_score_pairs32: pack and set scoring first");
+    if (!pi || !pj || !out || npairs < 0) return fail(BGCA_ERR_INVALID, "bgca_score_pairs32: bad arguments");
+    if (npairs == 0) return BGCA_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(e->device));
+    // translate ORIGINAL indices to sorted space on the host (lists are small on this path)
+    std::vector<int32_t> hi(npairs), hj(npairs);
+    CUDA_TRY(cudaMemcpyAsync(hi.data(), pi, sizeof(int32_t) * npairs, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(hj.data(), pj, sizeof(int32_t) * npairs, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int64_t k = 0; k < npairs; ++k) {
+        if (hi[k] < 0 || hi[k] >= e->n || hj[k] < 0 || hj[k] >= e->n)
+            return fail(BGCA_ERR_INVALID, "bgca_score_pairs32: index out of range");
+        hi[k] = e->inv_order[hi[k]];
+        hj[k] = e->inv_order[hj[k]];
+    }
+    CUDA_TRY(e->d_pq.reserve(npairs));
+    CUDA_TRY(e->d_ps.reserve(npairs));
+    CUDA_TRY(cudaMemcpyAsync(e->d_pq.p, hi.data(), sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->d_ps.p, hj.data(), sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    ScoreParams p;
+    fill_params(e, p, nullptr, nullptr, nullptr, 0);
+    e->last_launches = 0;
+    return run_s32_pairs(e, p, e->d_pq.p, e->d_ps.p, npairs, out, st);
+}
+
+int bgca_reduce_bgc(bgca_engine *e, const int32_t *rowbest, const int32_t *selfsc, int64_t *best,
+                    int64_t *selfsum, double *sim, void *stream)
+{
+    if (!e || !e->packed || !e->has_bgc) return fail(BGCA_ERR_INVALID, "bgca_reduce_bgc: pack with bgc_of_seq first");
+    if (!rowbest || !selfsc || !best || !selfsum) return fail(BGCA_ERR_INVALID, "bgca_reduce_bgc: NULL argument");
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(launch_bgc_reduce(rowbest, selfsc, e->d_bgc_start.p, e->d_bgc_doms.p, e->n_bgc, best, selfsum,
+                               sim, (cudaStream_t)stream));
+    return BGCA_OK;
+}
+
+int bgca_score_all_host(bgca_engine *e, const uint8_t *ascii, const int64_t *offsets, int32_t n,
+                        int32_t *scores_host)
+{
+    if (!e || !scores_host) return fail(BGCA_ERR_INVALID, "bgca_score_all_host: NULL argument");
+    int rc = bgca_pack(e, ascii, offsets, n, nullptr, nullptr, 0, 0, nullptr);
+    if (rc != BGCA_OK) return rc;
+    rc = bgca_plan(e, 0, 0, 1, nullptr);
+    if (rc != BGCA_OK) return rc;
+    int32_t *d_scores = nullptr;
+    const size_t bytes = sizeof(int32_t) * (size_t)n * (size_t)n;
+    CUDA_TRY(cudaMalloc(&d_scores, bytes));
+    cudaError_t err = cudaMemsetAsync(d_scores, 0, bytes, nullptr);
+    if (err == cudaSuccess) {
+        rc = bgca_score(e, d_scores, nullptr, nullptr, 0, nullptr);
+        if (rc == BGCA_OK) err = cudaMemcpy(scores_host, d_scores, bytes, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_scores);
+    if (rc != BGCA_OK) return rc;
+    if (err != cudaSuccess) return fail(BGCA_ERR_CUDA, std::string("bgca_score_all_host: ") + cudaGetErrorString(err));
+    return BGCA_OK;
+}
+
+int bgca_last_launches(const bgca_engine *e) { return e ? e->last_launches : 0; }
+
+int bgca_last_dp_ms(bgca_engine *e, float *ms)
+{
+    if (!e || !ms || !e->timed) return fail(BGCA_ERR_INVALID, "bgca_last_dp_ms: no timed bgca_score yet");
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaEventSynchronize(e->ev1));
+    CUDA_TRY(cudaEventElapsedTime(ms, e->ev0, e->ev1));
+    return BGCA_OK;
+}
+
+int bgca_dpx_probe(int device, double *out, int32_t n)
+{
+    if (!out || n <= 0) return fail(BGCA_ERR_INVALID, "bgca_dpx_probe: bad arguments");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        return fail(BGCA_ERR_CUDA, "bgca_dpx_probe: no usable CUDA device");
+    if (dpx_probe_run(device, out, n) != 0) return fail(BGCA_ERR_CUDA, "bgca_dpx_probe: CUDA failure");
+    return BGCA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,60 @@
+// Shared device/host declarations of the BGC aligner engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/bgca.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "bgclib_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace bgca {
+
+constexpr int NSYM = BGCA_NSYM;
+constexpr int CTA_THREADS = 256;  // 8 warps per CTA for every DP kernel
+
+// Everything a DP kernel needs; passed by value (fits the 4 KB param space).
+struct ScoreParams {
+    const uint8_t *codes;      // packed residues, sorted order, 16 B aligned per sequence
+    const uint32_t *seq_off;   // [n]   byte offset of each sorted sequence
+    const int32_t *seq_len;    // [n]
+    const int32_t *order;      // [n]   sorted -> original index
+    const int32_t *type_of;    // [n]   sorted -> type id   (nullable)
+    const int32_t *bgc_of;     // [n]   sorted -> BGC index (nullable)
+    const bgca_tile *tiles;    // tiles of ONE kernel variant
+    int32_t n_tiles;
+    int32_t *tile_counter;     // persistent-CTA work queue head
+    int32_t *scores;           // [n*n]      original space, nullable
+    int32_t *rowbest;          // [n*n_bgc]  original space, nullable
+    int32_t *selfsc;           // [n]        original space, nullable
+    int32_t n;
+    int32_t n_bgc;
+    int32_t open, extend;      // negative scores
+    int32_t type_check;
+    int8_t sub[NSYM * NSYM];
+};
+
+// K5 epilogue, fused into every DP kernel: one finished alignment (q, s) in
+// sorted space.  Emits only s >= q so that each unordered pair is written once
+// even though the packed halves also sweep the mirrored first pair.
+__device__ __forceinline__ void emit_pair(const ScoreParams &p, int q, int s, int32_t score)
+{
+    if (q < 0 || s < q) return;
+    const int oq = p.order[q], os = p.order[s];
+    if (p.scores) {
+        p.scores[(size_t)oq * p.n + os] = score;
+        p.scores[(size_t)os * p.n + oq] = score;
+    }
+    if (q == s) {
+        if (p.selfsc) p.selfsc[oq] = score;
+    }
+    if (p.rowbest) {
+        if (!p.type_check || p.type_of[q] == p.type_of[s]) {
+            atomicMax(&p.rowbest[(size_t)oq * p.n_bgc + p.bgc_of[s]], score);
+            if (q != s) atomicMax(&p.rowbest[(size_t)os * p.n_bgc + p.bgc_of[q]], score);
+        }
+    }
+}
+
+}  // namespace bgca

@@ -1,0 +1,53 @@
+// Instantiations of the packed DP kernel for one (G, MODE); compiled six times
+// (G in {8,16,32} x MODE in {local, global}) so the build parallelises.
+#include "gotoh_pair16.cuh"
+#include "launchers.h"
+#include "variants.h"
+
+#ifndef BGCA_INST_G
+#error "define BGCA_INST_G and BGCA_INST_MODE"
+#endif
+
+namespace bgca {
+
+template <int G, int K, int MODE>
+static cudaError_t launch_one(const ScoreParams &p, int n_sm, cudaStream_t st, int *grid_out)
+{
+    using Cfg = Pair16Cfg<G, K>;
+    static int ctas_per_sm = 0;   // per instantiation, resolved on first use
+    auto kern = gotoh_pair16_kernel<G, K, MODE>;
+    if (ctas_per_sm == 0) {
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               Cfg::SMEM_BYTES);
+        if (err != cudaSuccess) return err;
+        int occ = 0;
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CTA_THREADS, Cfg::SMEM_BYTES);
+        if (err != cudaSuccess) return err;
+        ctas_per_sm = occ > 0 ? occ : 1;
+    }
+    int grid = n_sm * ctas_per_sm;
+    if (grid > p.n_tiles) grid = p.n_tiles;
+    if (grid_out) *grid_out = grid;
+    kern<<<grid, CTA_THREADS, Cfg::SMEM_BYTES, st>>>(p);
+    return cudaGetLastError();
+}
+
+#define BGCA_CAT2(a, b, c, d) a##b##c##d
+#define BGCA_CAT(a, b, c, d) BGCA_CAT2(a, b, c, d)
+
+cudaError_t BGCA_CAT(launch_pair16_g, BGCA_INST_G, _m, BGCA_INST_MODE)(int K, const ScoreParams &p,
+                                                                      int n_sm, cudaStream_t st,
+                                                                      int *grid_out)
+{
+    switch (K) {
+#define X(G, KK) \
+    case KK:     \
+        return launch_one<BGCA_INST_G, KK, BGCA_INST_MODE>(p, n_sm, st, grid_out);
+        BGCA_K_LIST(X, BGCA_INST_G)
+#undef X
+        default:
+            return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace bgca

@@ -1,0 +1,158 @@
+// Calibration microbenchmark: issue rate of the DPX / ALU instructions the DP
+// kernels are built from, in lane-ops per clock per SM (the
+// guides give no DPX rate for sm_100a, so the build measures it).
+//
+// Each thread runs NCH independent chains x_i = op(x_i, x_{i+1}, a) so the
+// compiler can neither fold nor hoist; the grid is 2 CTAs of 512 threads per
+// SM (32 warps/SM), every CTA times itself with clock64 and the slowest CTA
+// defines the rate.
+#include "launchers.h"
+
+namespace bgca {
+
+constexpr int NCH = 8;
+constexpr int PROBE_ITERS = 4096;
+
+template <int OP>
+__device__ __forceinline__ uint32_t probe_op(uint32_t x, uint32_t y, uint32_t a)
+{
+    if (OP == 0) return __viaddmax_s16x2(x, a, y);
+    if (OP == 1) return __vimax3_s16x2(x, y, a);
+    if (OP == 2) return __vmaxs2(x, y);
+    if (OP == 3) return __vadd2(x, y);
+    if (OP == 4) return x + y + a;
+    if (OP == 5) return x * a + y;
+    if (OP == 6) return __byte_perm(x, y, a);
+    if (OP == 7) return (uint32_t)__viaddmax_s32((int)x, (int)a, (int)y);
+    return x;
+}
+
+template <int OP>
+__global__ void __launch_bounds__(512) probe_kernel(uint32_t a, uint32_t seed, uint32_t *sink,
+                                                    long long *cycles)
+{
+    uint32_t x[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) x[i] = seed * (threadIdx.x + 1) + i * 0x9E3779B9u;
+    __syncthreads();
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < PROBE_ITERS; ++it) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int i = 0; i < NCH; ++i) x[i] = probe_op<OP>(x[i], x[(i + 1) % NCH], a);
+        }
+    }
+    const long long t1 = clock64();
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) acc ^= x[i];
+    if (acc == 0x12345678u) sink[0] = acc;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+// OP 8: the packed local cell recurrence exactly as in gotoh_pair16.cuh
+// (K = 8 rows, profile words from registers) — the practical ceiling of the
+// inner loop without shared-memory, shuffle or loop overhead.
+__global__ void __launch_bounds__(512) probe_cell_kernel(uint32_t ext2, uint32_t open2, uint32_t seed,
+                                                         uint32_t *sink, long long *cycles)
+{
+    constexpr int K = 8;
+    uint32_t Hp[K], Eh[K], P[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        Hp[k] = 0; Eh[k] = 0;
+        P[k] = (seed * (threadIdx.x + 3 + k)) & 0x00070007u;
+    }
+    uint32_t best = 0, hin_prev = 0, h_in = seed & 0x000F000Fu, f_in = 0;
+    __syncthreads();
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < PROBE_ITERS; ++it) {
+        uint32_t diag = hin_prev;
+        hin_prev = h_in;
+        uint32_t up = h_in, F = f_in;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            Eh[k] = __viaddmax_s16x2(Eh[k], ext2, Hp[k]);
+            F = __viaddmax_s16x2(F, ext2, up);
+            const uint32_t u = __vmaxs2(Eh[k], F);
+            const uint32_t tt = __vadd2(diag, P[k]);
+            const uint32_t h = __viaddmax_s16x2_relu(u, open2, tt);
+            diag = Hp[k];
+            Hp[k] = h;
+            if (k & 1) best = __vimax3_s16x2(best, up, h);
+            up = h;
+        }
+        h_in = up ^ (uint32_t)it;   // keep the next step dependent on this one
+        f_in = F;
+    }
+    const long long t1 = clock64();
+    if (best == 0x12345678u) sink[0] = best;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int OP>
+static double run_op(int n_sm, uint32_t *sink, long long *d_cycles, long long *h_cycles)
+{
+    const int grid = n_sm * 2;
+    probe_kernel<OP><<<grid, 512>>>(0x00030005u, 12345u, sink, d_cycles);   // warm-up
+    probe_kernel<OP><<<grid, 512>>>(0x00030005u, 12345u, sink, d_cycles);
+    if (cudaMemcpy(h_cycles, d_cycles, sizeof(long long) * grid, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return -1.0;
+    long long worst = 0;
+    for (int i = 0; i < grid; ++i) worst = h_cycles[i] > worst ? h_cycles[i] : worst;
+    const double lane_ops_per_sm = 1024.0 * NCH * 4.0 * PROBE_ITERS;
+    return lane_ops_per_sm / (double)worst;
+}
+
+int dpx_probe_run(int device, double *out, int n)
+{
+    if (cudaSetDevice(device) != cudaSuccess) return -1;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1;
+    const int n_sm = prop.multiProcessorCount;
+    const int grid = n_sm * 2;
+    uint32_t *sink = nullptr;
+    long long *d_cycles = nullptr;
+    if (cudaMalloc(&sink, 64) != cudaSuccess) return -1;
+    if (cudaMalloc(&d_cycles, sizeof(long long) * grid) != cudaSuccess) return -1;
+    long long *h_cycles = new long long[grid];
+    double r[10] = {0};
+    r[0] = run_op<0>(n_sm, sink, d_cycles, h_cycles);
+    r[1] = run_op<1>(n_sm, sink, d_cycles, h_cycles);
+    r[2] = run_op<2>(n_sm, sink, d_cycles, h_cycles);
+    r[3] = run_op<3>(n_sm, sink, d_cycles, h_cycles);
+    r[4] = run_op<4>(n_sm, sink, d_cycles, h_cycles);
+    r[5] = run_op<5>(n_sm, sink, d_cycles, h_cycles);
+    r[6] = run_op<6>(n_sm, sink, d_cycles, h_cycles);
+    r[7] = run_op<7>(n_sm, sink, d_cycles, h_cycles);
+    {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        probe_cell_kernel<<<grid, 512>>>(0xFFFFFFFFu, 0xFFF4FFF4u, 777u, sink, d_cycles);
+        cudaEventRecord(e0);
+        probe_cell_kernel<<<grid, 512>>>(0xFFFFFFFFu, 0xFFF4FFF4u, 777u, sink, d_cycles);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaMemcpy(h_cycles, d_cycles, sizeof(long long) * grid, cudaMemcpyDeviceToHost);
+        long long worst = 0;
+        for (int i = 0; i < grid; ++i) worst = h_cycles[i] > worst ? h_cycles[i] : worst;
+        r[8] = 1024.0 * (8 * 5.5) * PROBE_ITERS / (double)worst;
+        r[9] = (double)worst / (ms * 1e3);   // cycles per microsecond = MHz (kernel ~ whole event span)
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    delete[] h_cycles;
+    cudaFree(sink);
+    cudaFree(d_cycles);
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    for (int i = 0; i < n && i < 10; ++i) out[i] = r[i];
+    return 0;
+}
+
+}  // namespace bgca

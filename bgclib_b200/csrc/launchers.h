@@ -1,0 +1,32 @@
+// Host-side launch entry points of the per-(G, MODE) kernel translation units.
+#pragma once
+#include "common.cuh"
+
+namespace bgca {
+
+#define BGCA_DECL_LAUNCH(G, M)                                                               \
+    cudaError_t launch_pair16_g##G##_m##M(int K, const ScoreParams &p, int n_sm, cudaStream_t st, \
+                                          int *grid_out);
+BGCA_DECL_LAUNCH(8, 0)
+BGCA_DECL_LAUNCH(8, 1)
+BGCA_DECL_LAUNCH(16, 0)
+BGCA_DECL_LAUNCH(16, 1)
+BGCA_DECL_LAUNCH(32, 0)
+BGCA_DECL_LAUNCH(32, 1)
+#undef BGCA_DECL_LAUNCH
+
+cudaError_t launch_s32(int mode, const ScoreParams &p, const int32_t *pq, const int32_t *ps,
+                       long long npairs, int2 *scratch, int scratch_stride, int32_t *out_list,
+                       int grid, cudaStream_t st);
+
+// K1 / K5 kernels (pack_reduce.cu)
+cudaError_t launch_pack(const uint8_t *ascii, const int64_t *offsets_orig, const int32_t *order,
+                        const uint32_t *seq_off, const int32_t *seq_len, int32_t n, uint8_t *codes,
+                        unsigned long long *err_word, cudaStream_t st);
+cudaError_t launch_bgc_reduce(const int32_t *rowbest, const int32_t *selfsc, const int32_t *bgc_start,
+                              const int32_t *bgc_doms, int32_t n_bgc, int64_t *best, int64_t *selfsum,
+                              double *sim, cudaStream_t st);
+
+int dpx_probe_run(int device, double *out, int n);
+
+}  // namespace bgca

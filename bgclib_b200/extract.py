@@ -1,0 +1,187 @@
+"""Walks unchanged (duck-typed) BGClib objects and flattens them into the arrays
+the engine packs.  Nothing is attached to, or mutated on, the reference objects
+(they get pickled by BGCtoolkit.py:1249,1255,1354).
+
+Reference contract followed:
+  * unit aligned = ``BGCDomain.get_sequence()`` = ``protein.sequence[ali_from:ali_to]``
+    (BGClib/BGClib.py:3240-3241); the sequence setter already upper-cased it
+    (BGClib/BGClib.py:1903-1907)
+  * container walk: ``BGCCollection.bgcs`` (dict id -> BGC, insertion order,
+    BGClib/BGClib.py:755) -> ``BGC.protein_list`` (:899) -> ``BGCProtein.domain_list``
+    (:1881, ordered by ali_from after filter_domains :2132)
+  * ``cbp_only``: only proteins listed in ``BGC.CBPcontent`` (type -> [BGCProtein],
+    :889-891), the selection ``save_fasta`` makes (BGCtoolkit.py:1431-1436)
+  * domain type key: external alias dict first, then the domain's own alias,
+    then its ID — the label precedence of ``domain_string``
+    (BGClib/BGClib.py:1991-2002) and the ID-or-alias match of BGCtoolkit.py:1511-1513
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Iterable, List, Optional, Sequence
+
+import numpy as np
+
+
+@dataclass(frozen=True)
+class DomainRecord:
+    """Row/column identity of the domain-pair matrix."""
+    index: int
+    bgc_id: str
+    protein_identifier: str
+    domain_id: str
+    type_key: str
+    ali_from: int
+    ali_to: int
+    length: int
+
+
+@dataclass
+class DomainBatch:
+    sequences: List[str]
+    records: List[DomainRecord]
+    bgc_ids: List[str]                     # row/column identity of the BGC matrix
+    bgc_of_seq: np.ndarray                 # int32[n]
+    type_names: List[str]
+    type_of_seq: np.ndarray                # int32[n]
+    skipped: List[str] = field(default_factory=list)   # human-readable notes (empty domains ...)
+
+    def __len__(self):
+        return len(self.sequences)
+
+
+def type_key(domain, alias: Optional[dict]) -> str:
+    if alias:
+        try:
+            return alias[domain.ID]
+        except KeyError:
+            pass
+    a = getattr(domain, "alias", "")
+    return a if a != "" else domain.ID
+
+
+def _is_collection(obj):
+    return hasattr(obj, "bgcs") and isinstance(getattr(obj, "bgcs"), dict)
+
+
+def _is_bgc(obj):
+    return hasattr(obj, "protein_list") and hasattr(obj, "CBPcontent")
+
+
+def _is_protein_collection(obj):
+    return hasattr(obj, "proteins") and isinstance(getattr(obj, "proteins"), dict) and not _is_bgc(obj)
+
+
+def _is_protein(obj):
+    return hasattr(obj, "domain_list") and hasattr(obj, "sequence")
+
+
+def _is_domain(obj):
+    return hasattr(obj, "ali_from") and hasattr(obj, "get_sequence")
+
+
+def _bgc_proteins(bgc, cbp_only: bool):
+    if not cbp_only:
+        return list(bgc.protein_list)
+    chosen = {id(p) for plist in bgc.CBPcontent.values() for p in plist}
+    # keep the 5'-3' order of protein_list, as save_fasta's callers see it
+    return [p for p in bgc.protein_list if id(p) in chosen]
+
+
+def extract(source, *, unit: str = "domain", cbp_only: bool = True, alias: Optional[dict] = None,
+            domain_types: Optional[Iterable[str]] = None) -> DomainBatch:
+    """Flatten ``source`` into a DomainBatch.
+
+    source: BGCCollection | BGC | ProteinCollection | iterable of BGC / BGCProtein /
+            BGCDomain / str | dict name -> str.
+    unit:   "domain"  — one entry per BGCDomain (get_sequence());
+            "protein" — one entry per BGCProtein (whole sequence; the form the
+                        reference's own domain FASTA exports load back as,
+                        e.g. examples/all_KS_domains.fasta).
+    domain_types: optional set of type keys to keep (e.g. {"KS"}).
+    """
+    if unit not in ("domain", "protein"):
+        raise ValueError("unit must be 'domain' or 'protein'")
+    keep = set(domain_types) if domain_types is not None else None
+
+    seqs: List[str] = []
+    recs: List[DomainRecord] = []
+    bgc_ids: List[str] = []
+    bgc_index = {}
+    bgc_of: List[int] = []
+    type_names: List[str] = []
+    type_index = {}
+    type_of: List[int] = []
+    skipped: List[str] = []
+
+    def bgc_slot(name: str) -> int:
+        if name not in bgc_index:
+            bgc_index[name] = len(bgc_ids)
+            bgc_ids.append(name)
+        return bgc_index[name]
+
+    def type_slot(name: str) -> int:
+        if name not in type_index:
+            type_index[name] = len(type_names)
+            type_names.append(name)
+        return type_index[name]
+
+    def add(seq: str, bgc_name: str, prot_id: str, dom_id: str, tkey: str, a0: int, a1: int):
+        if keep is not None and tkey not in keep:
+            return
+        if len(seq) == 0:
+            skipped.append(f"{prot_id}:{dom_id}[{a0}:{a1}] has an empty sequence")
+            return
+        recs.append(DomainRecord(len(seqs), bgc_name, prot_id, dom_id, tkey, a0, a1, len(seq)))
+        seqs.append(seq)
+        bgc_of.append(bgc_slot(bgc_name))
+        type_of.append(type_slot(tkey))
+
+    def add_protein(p, bgc_name: Optional[str]):
+        name = bgc_name if bgc_name is not None else (getattr(p, "parent_cluster_id", "") or p.identifier)
+        if unit == "protein":
+            tkey = getattr(p, "protein_type", "") or "protein"
+            add(p.sequence, name, p.identifier, "", tkey, 0, len(p.sequence))
+            return
+        for d in p.domain_list:
+            add(d.get_sequence(), name, p.identifier, d.ID, type_key(d, alias), d.ali_from, d.ali_to)
+
+    def add_bgc(bgc):
+        bgc_slot(bgc.identifier)   # BGCs without eligible domains still get a (zero) row
+        for p in _bgc_proteins(bgc, cbp_only):
+            add_protein(p, bgc.identifier)
+
+    if _is_collection(source):
+        for bgc in source.bgcs.values():
+            add_bgc(bgc)
+    elif _is_bgc(source):
+        add_bgc(source)
+    elif _is_protein_collection(source):
+        for p in source.proteins.values():
+            add_protein(p, None)
+    elif isinstance(source, dict):
+        for name, s in source.items():
+            add(_norm(s), str(name), str(name), "", "sequence", 0, len(s))
+    else:
+        for i, item in enumerate(source):
+            if _is_bgc(item):
+                add_bgc(item)
+            elif _is_protein(item):
+                add_protein(item, None)
+            elif _is_domain(item):
+                p = item.protein
+                name = getattr(p, "parent_cluster_id", "") or p.identifier
+                add(item.get_sequence(), name, p.identifier, item.ID, type_key(item, alias),
+                    item.ali_from, item.ali_to)
+            elif isinstance(item, str):
+                add(_norm(item), f"seq{i}", f"seq{i}", "", "sequence", 0, len(item))
+            else:
+                raise TypeError(f"cannot extract sequences from {type(item).__name__}")
+
+    return DomainBatch(seqs, recs, bgc_ids, np.asarray(bgc_of, dtype=np.int32), type_names,
+                       np.asarray(type_of, dtype=np.int32), skipped)
+
+
+def _norm(s: str) -> str:
+    """Same normalisation as the reference's sequence setter (BGClib/BGClib.py:1906)."""
+    return s.replace("\n", "").strip().replace(" ", "").upper()

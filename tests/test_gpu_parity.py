@@ -1,0 +1,261 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle — bit-exact
+integer scores.  Run on the B200 box:  python -m pytest tests -m gpu -x -q"""
+import hashlib
+
+import numpy as np
+import pytest
+
+import oracle
+from bgclib_b200 import bgc_similarity, domain_pair_scores, extract, get_engine, synth
+from fakes import build_collection
+
+pytestmark = pytest.mark.gpu
+
+AA = "ARNDCQEGHILKMFPSTWYV"
+
+
+def _rand(rng, n, letters=AA):
+    return "".join(rng.choice(list(letters), size=int(n)))
+
+
+def _related(rng, n_fam, fam_size, lo, hi, letters=AA):
+    out = []
+    for _ in range(n_fam):
+        anc = list(_rand(rng, rng.integers(lo, hi + 1), letters))
+        for _ in range(fam_size):
+            m = anc.copy()
+            for _ in range(int(len(m) * rng.uniform(0.05, 0.5))):
+                m[int(rng.integers(0, len(m)))] = letters[int(rng.integers(0, len(letters)))]
+            if rng.random() < 0.7:
+                p = int(rng.integers(0, len(m)))
+                k = int(rng.integers(1, 9))
+                m = m[:p] + list(_rand(rng, k, letters)) + m[p:] if rng.random() < 0.5 else m[:p] + m[p + k:]
+            out.append("".join(m) if len(m) > 0 else "A")
+    return out
+
+
+# ---- config 1: the reference's own fixture, four parameter settings ------------------------
+@pytest.mark.parametrize("key", ["local_12_1", "global_12_1", "local_11_1", "global_11_1"])
+def test_config1_ks_domains_golden(ks_records, ks_golden, key):
+    g = ks_golden[key]
+    seqs = [r["sequence"] for r in ks_records]
+    res = domain_pair_scores(seqs, mode=g["mode"], open_gap_score=g["open"], extend_gap_score=g["extend"])
+    assert res.scores.dtype == np.int32 and res.scores.shape == (15, 15)
+    assert (res.scores == np.array(g["matrix"], dtype=np.int32)).all()
+    assert hashlib.sha256(res.scores.astype("<i4").tobytes()).hexdigest() == g["sha256_int32_le"]
+    assert res.plan["total_pairs"] == 120
+
+
+# ---- random / related sequences over every group width and many row counts -----------------
+@pytest.mark.parametrize("mode", ["local", "global"])
+@pytest.mark.parametrize("lo,hi", [(1, 16), (20, 70), (60, 140), (200, 300), (380, 460), (500, 640), (900, 1024)])
+def test_random_lengths_bit_exact(mode, lo, hi):
+    rng = np.random.default_rng(lo * 7 + hi + (mode == "global"))
+    seqs = _related(rng, 4, 6, lo, hi) + [_rand(rng, rng.integers(lo, hi + 1)) for _ in range(9)]
+    seqs = [s[:hi] for s in seqs]
+    res = domain_pair_scores(seqs, mode=mode)
+    want = oracle.all_pairs(seqs, mode=oracle.MODE_LOCAL if mode == "local" else oracle.MODE_GLOBAL)
+    assert (res.scores == want).all()
+    assert res.plan["n_fallback32"] == 0
+
+
+@pytest.mark.parametrize("force_g", ["8", "16", "32"])
+def test_every_group_width(monkeypatch, force_g):
+    monkeypatch.setenv("BGCA_FORCE_G", force_g)
+    rng = np.random.default_rng(int(force_g))
+    seqs = _related(rng, 5, 5, 30, 250) + [_rand(rng, n) for n in (1, 2, 3, 31, 32, 33, 64, 255, 256)]
+    for mode, cm in (("local", 0), ("global", 1)):
+        res = domain_pair_scores(seqs, mode=mode)
+        assert (res.scores == oracle.all_pairs(seqs, mode=cm)).all()
+
+
+def test_mixed_lengths_and_ambiguity_letters():
+    rng = np.random.default_rng(99)
+    letters = "ARNDCQEGHILKMFPSTWYVBZX*"
+    seqs = _related(rng, 6, 5, 40, 600, letters) + ["*", "X", "BZ", "W" * 100]
+    for mode, cm in (("local", 0), ("global", 1)):
+        for o, e in ((-12, -1), (-11, -1), (-5, -2), (-3, -3)):
+            res = domain_pair_scores(seqs, mode=mode, open_gap_score=o, extend_gap_score=e)
+            want = oracle.all_pairs(seqs, mode=cm, open_gap=o, extend_gap=e)
+            assert (res.scores == want).all(), (mode, o, e)
+
+
+def test_long_sequences_take_the_32bit_kernel():
+    rng = np.random.default_rng(5)
+    base = _rand(rng, 3300)
+    seqs = [base[:1500], base[200:3300], _rand(rng, 1100), base[1000:2100], _rand(rng, 300), base[:257],
+            "W" * 3200, "WY" * 1550]
+    for mode, cm in (("local", 0), ("global", 1)):
+        res = domain_pair_scores(seqs, mode=mode)
+        assert res.plan["n_fallback32"] > 0
+        assert (res.scores == oracle.all_pairs(seqs, mode=cm)).all()
+    # the poly-W self score (3200 * 11) exceeds int16: only the 32-bit path can hold it
+    loc = domain_pair_scores(seqs, mode="local").scores
+    assert loc[6, 6] == 35200
+
+
+def test_pair_list_32bit_kernel():
+    rng = np.random.default_rng(6)
+    seqs = _related(rng, 3, 4, 100, 700)
+    eng = get_engine()
+    for mode, cm in (("local", 0), ("global", 1)):
+        eng.set_scoring(mode=mode)
+        eng.pack(seqs)
+        pi = rng.integers(0, len(seqs), 64)
+        pj = rng.integers(0, len(seqs), 64)
+        got = eng.score_pairs32(pi, pj).cpu().numpy()
+        assert (got == oracle.pair_list(seqs, pi, pj, mode=cm)).all()
+
+
+def test_packer_matches_oracle_encoding():
+    rng = np.random.default_rng(8)
+    seqs = [_rand(rng, n, "ARNDCQEGHILKMFPSTWYVBZX*") for n in (1, 15, 16, 17, 33, 250, 64, 5, 480)]
+    eng = get_engine()
+    eng.pack(seqs)
+    codes, offs, order = eng.get_packed()
+    lens = np.array([len(s) for s in seqs])
+    assert (lens[order] == np.sort(lens)).all() and sorted(order.tolist()) == list(range(len(seqs)))
+    for r, o in enumerate(order):
+        seg = codes[offs[r]:offs[r + 1]]
+        assert offs[r] % 16 == 0 and len(seg) == (lens[o] + 15) // 16 * 16
+        assert (seg[: lens[o]] == oracle.encode(seqs[o])).all()
+        assert (seg[lens[o]:] == 24).all()
+
+
+def test_errors_mirror_biopython():
+    with pytest.raises(ValueError, match="alphabet"):
+        domain_pair_scores(["ACDEFG", "ACDUFG"])
+    with pytest.raises(ValueError, match="alphabet"):
+        get_engine().pack(["ACDEFG", "acdefg"])       # the engine itself does not upper-case
+    with pytest.raises(ValueError, match="zero length"):
+        get_engine().pack(["ACD", ""])
+    with pytest.raises(ValueError):
+        domain_pair_scores([])
+    with pytest.raises(ValueError):
+        domain_pair_scores(["ACD"], open_gap_score=-1, extend_gap_score=-5)
+    with pytest.raises(ValueError):
+        domain_pair_scores(["ACD"], open_gap_score=-11.5)
+    # the engine is still usable after a failed call
+    assert domain_pair_scores(["WW", "WW"]).scores.tolist() == [[22, 22], [22, 22]]
+
+
+# ---- config 2: 37 Af293 BGCs -> BGC-pair similarity ----------------------------------------
+def _af293_collection(af293, ks_records, seed=20260102):
+    """Config 2b: the 282-domain architecture of the 57 CBPs with the real
+    KS sequences where they exist and seeded synthetic sequences for every other domain."""
+    rng = np.random.default_rng(seed)
+    ks_by_protein = {}
+    for r in ks_records:
+        ks_by_protein.setdefault(r["protein_identifier"], []).append(r["sequence"])
+    length = {"KS": 253, "KS_C": 119, "KS_Ce": 112, "AT": 319, "C": 457, "A": 424, "A_C": 76, "DH": 298,
+              "KR": 180, "SAT": 240, "ER": 313, "PT": 329, "DMAT": 363, "T/ACP": 70}
+    anc = {}
+    spec = {b: [] for b in af293["bgcs"]}
+    for cbp in af293["cbps"]:
+        seq, doms, pos = "M", [], 1
+        real = list(ks_by_protein.get(cbp["protein_identifier"], []))
+        for t in cbp["domains"]:
+            if t == "KS" and real:
+                s = real.pop(0)
+            else:
+                L = length.get(t, 150)
+                if t not in anc:
+                    anc[t] = _rand(rng, L)
+                m = list(anc[t])
+                for _ in range(int(L * rng.uniform(0.1, 0.6))):
+                    m[int(rng.integers(0, L))] = AA[int(rng.integers(0, 20))]
+                s = "".join(m)
+            linker = _rand(rng, rng.integers(3, 12))
+            doms.append((t, t, pos, pos + len(s)))
+            seq += s + linker
+            pos += len(s) + len(linker)
+        spec[cbp["bgc"]].append((cbp["protein_identifier"], seq, doms))
+    return build_collection(spec)
+
+
+@pytest.mark.parametrize("same_type_only", [True, False])
+def test_config2_af293_bgc_similarity(af293, ks_records, same_type_only):
+    col = _af293_collection(af293, ks_records)
+    batch = extract(col)
+    assert len(batch) == 282 and len(batch.bgc_ids) == 37
+    res = bgc_similarity(col, same_type_only=same_type_only, bgc_ids=af293["bgcs"])
+    scores = oracle.all_pairs(batch.sequences)
+    sim, best, selfs, _ = oracle.bgc_similarity_np(scores, batch.bgc_of_seq, batch.type_of_seq, 37,
+                                                   same_type_only=same_type_only)
+    assert res.bgc_ids == af293["bgcs"]
+    assert (res.best == best).all() and (res.self_score == selfs).all()
+    assert (res.sim == sim).all()                      # one correctly-rounded f64 divide: bit-exact
+    assert res.sim.min() >= 0 and res.sim.max() <= 1.0 and (np.diag(res.sim)[selfs > 0] == 1.0).all()
+    assert (res.sim[selfs == 0] == 0).all()            # BGCs without CBP domains: zero rows
+    # the fused path equals the unfused one built from the materialised matrix
+    dps = domain_pair_scores(col, same_type_only=same_type_only)
+    if same_type_only:
+        same = batch.type_of_seq[:, None] == batch.type_of_seq[None, :]
+        assert (dps.computed == same).all()
+        assert (dps.scores[same] == scores[same]).all() and (dps.scores[~same] == 0).all()
+    else:
+        assert (dps.scores == scores).all()
+
+
+def test_config2a_ks_only(af293, ks_records):
+    spec = {b: [] for b in af293["bgcs"]}
+    for r in ks_records:
+        spec[r["bgc"]].append((r["identifier"], r["sequence"], [("ketoacyl-synt", "KS", 0, len(r["sequence"]))]))
+    col = build_collection(spec)
+    res = bgc_similarity(col, bgc_ids=af293["bgcs"])
+    nonempty = res.self_score > 0
+    assert int(nonempty.sum()) == 13 and (np.diag(res.sim)[nonempty] == 1.0).all()
+    assert (res.sim[~nonempty] == 0).all() and (res.sim[:, ~nonempty] == 0).all()
+    seqs = [r["sequence"] for r in ks_records]
+    bgc_of = np.array([af293["bgcs"].index(r["bgc"]) for r in ks_records])
+    sim, best, selfs, _ = oracle.bgc_similarity_np(oracle.all_pairs(seqs), bgc_of, np.zeros(15, int), 37)
+    assert (res.sim == sim).all() and (res.best == best).all()
+
+
+# ---- multi-rank logic on one GPU: ranks' tile shares run one after another -------------------
+def test_rank_shares_combine_to_single_rank_result():
+    import torch
+    col = synth.ks_like(96, lo=60, hi=200, mean=120, sd=30)
+    seqs = col.sequences()
+    eng = get_engine()
+    eng.set_scoring()
+    eng.pack(seqs)
+    n = len(seqs)
+    parts, pairs = [], 0
+    for r in range(4):
+        info = eng.plan(rank=r, world=4)
+        pairs += info["n_pairs"]
+        m = torch.full((n, n), -2**31, dtype=torch.int32, device=eng.tdev)
+        eng.score(scores=m)
+        parts.append(m)
+    assert pairs == n * (n + 1) // 2
+    combined = torch.stack(parts).max(dim=0).values.cpu().numpy()     # what all_reduce(MAX) yields
+    stacked = torch.stack(parts)
+    assert ((stacked != -2**31).sum(dim=0) == 1).all()                # every entry owned by exactly one rank
+    assert (combined == oracle.all_pairs(seqs)).all()
+
+
+# ---- full-size properties (config 3 scale is too big for the oracle: sample + invariants) ---
+def test_config3_scale_sample_and_invariants():
+    col = synth.ks_like(2000)
+    seqs = col.sequences()
+    res = domain_pair_scores(seqs)
+    m = res.scores
+    assert (m == m.T).all() and (m >= 0).all()
+    sub = oracle.BLOSUM62.astype(int)
+    codes = [oracle.encode(s) for s in seqs]
+    assert (np.diag(m) == np.array([int(sub[c, c].sum()) for c in codes])).all()   # self score = sum diag
+    assert (m <= np.minimum.outer(np.diag(m), np.diag(m))).all()                   # s(d,e) <= min self
+    rng = np.random.default_rng(0)
+    pi, pj = rng.integers(0, 2000, 3000), rng.integers(0, 2000, 3000)
+    assert (m[pi, pj] == oracle.pair_list(seqs, pi, pj)).all()
+    assert res.plan["cells"] == col.pair_stats()["cells"]
+
+
+def test_e2e_host_call_matches():
+    col = synth.ks_like(64, lo=100, hi=180, mean=140, sd=20)
+    eng = get_engine()
+    eng.set_scoring()
+    out = eng.score_all_host(col.ascii, col.offsets)
+    assert (out == oracle.all_pairs(col.sequences())).all()
+    assert eng.last_launches() >= 1 and eng.last_dp_ms() > 0

@@ -1,0 +1,193 @@
+"""Host-side logic that needs no GPU: the C ABI loads and exports what
+include/bgca.h declares, the K6 planner's partition properties, extraction from
+(fake) reference objects, the synthetic generators, and the pure-Python model of
+the kernel's systolic data flow against the oracle."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+from bgclib_b200 import engine as eng
+from bgclib_b200 import extract, plan_host, synth
+from bgclib_b200.alphabet import resolve_matrix
+from fakes import FakeProteinCollection, FakeProtein, build_collection
+from systolic_model import systolic_score
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "bgca.h").read_text()
+    declared = set(re.findall(r"\b(bgca_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(eng.EXPORTED_SYMBOLS)
+    lib = eng.load_library()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.bgca_version() == 100
+
+
+def test_no_device_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = eng.load_library()
+    h = ctypes.c_void_p()
+    rc = lib.bgca_create(0, ctypes.byref(h))
+    assert rc == eng.BGCA_ERR_CUDA and b"no CPU fallback" in lib.bgca_last_error()
+    with pytest.raises(RuntimeError):
+        eng.Engine(0)
+    out = (ctypes.c_double * 10)()
+    assert lib.bgca_dpx_probe(0, out, 10) == eng.BGCA_ERR_CUDA
+
+
+def _expand(tiles):
+    """tiles -> list of unique (i<=j) pairs exactly as the kernel epilogue emits them."""
+    pairs = []
+    for t in tiles:
+        for s in range(t["s_begin"], t["s_end"]):
+            for q in (t["qa"], t["qb"]):
+                if q >= 0 and s >= q:
+                    pairs.append((q, s))
+    return pairs
+
+
+@pytest.mark.parametrize("n,world", [(1, 1), (2, 1), (7, 1), (64, 1), (301, 2), (500, 8)])
+def test_planner_every_pair_exactly_once(n, world):
+    rng = np.random.default_rng(n)
+    lens = np.sort(rng.integers(30, 700, size=n)).astype(np.int32)
+    seen = []
+    total = None
+    for r in range(world):
+        tiles, info = plan_host(lens, rank=r, world=world)
+        pairs = _expand(tiles)
+        assert info["n_pairs"] == len(pairs)
+        assert info["cells"] == sum(int(lens[i]) * int(lens[j]) for i, j in pairs)
+        total = info["total_pairs"]
+        seen += pairs
+    assert total == n * (n + 1) // 2
+    assert len(seen) == total and len(set(seen)) == total
+    assert set(seen) == {(i, j) for i in range(n) for j in range(i, n)}
+
+
+def test_planner_same_type_blocks():
+    rng = np.random.default_rng(5)
+    types = np.sort(rng.integers(0, 4, size=200)).astype(np.int32)
+    lens = np.zeros(200, np.int32)
+    for t in range(4):
+        m = types == t
+        lens[m] = np.sort(rng.integers(60, 500, size=int(m.sum())))
+    tiles, info = plan_host(lens, types, same_type_only=True)
+    pairs = set(_expand(tiles))
+    want = {(i, j) for i in range(200) for j in range(i, 200) if types[i] == types[j]}
+    assert pairs == want and info["total_pairs"] == len(want)
+
+
+def test_planner_balance_and_variants():
+    lens = np.sort(np.random.default_rng(0).integers(360, 481, size=4000)).astype(np.int32)
+    loads = []
+    for r in range(8):
+        tiles, info = plan_host(lens, rank=r, world=8)
+        loads.append(info["cells_computed"])
+        for v in set(tiles["variant"].tolist()):
+            G, K = v >> 8, v & 0xFF
+            sel = tiles[tiles["variant"] == v]
+            lq = np.maximum(lens[sel["qa"]], np.where(sel["qb"] >= 0, lens[np.maximum(sel["qb"], 0)], 0))
+            assert G in (8, 16, 32) and (G * K >= lq).all()
+    assert max(loads) / (sum(loads) / 8) < 1.01          # LPT on exact cell counts
+    # sequences beyond the packed kernel's reach (or int16) go to the 32-bit kernel
+    tiles, info = plan_host(np.array([100, 200, 1500, 3200], np.int32))
+    by_q = {int(t["qa"]): int(t["variant"]) for t in tiles}
+    assert by_q[0] != 0 or info["n_fallback32"] >= 1
+    assert by_q[2] == 0 and info["n_fallback32"] >= 1
+    # global mode: a huge gap-extension penalty leaves int16 -> fallback
+    _, info_g = plan_host(np.array([400, 420], np.int32), mode=1, open_gap=-40, extend_gap=-40)
+    assert info_g["n_fallback32"] == info_g["n_tiles"]
+
+
+def test_extract_from_collection():
+    p1 = "M" + "ACDEFGHIKL" * 6
+    p2 = "MNPQRSTVWY" * 5
+    spec = {
+        "bgcA": [("bgcA~L0+CDS1", p1, [("ketoacyl-synt", "KS", 1, 31), ("Acyl_transf_1", "AT", 31, 61)])],
+        "bgcB": [("bgcB~L0+CDS1", p2, [("ketoacyl-synt", "", 0, 25)]),
+                 ("bgcB~L0+CDS2", p1, [("PP-binding", "T/ACP", 5, 5)])],      # empty slice
+        "bgcC": [],
+    }
+    col = build_collection(spec)
+    b = extract(col, alias={"ketoacyl-synt": "KS"})
+    assert b.bgc_ids == ["bgcA", "bgcB", "bgcC"]
+    assert [r.type_key for r in b.records] == ["KS", "AT", "KS"]
+    assert b.sequences == [p1[1:31], p1[31:61], p2[0:25]]
+    assert b.bgc_of_seq.tolist() == [0, 0, 1]
+    assert b.type_of_seq.tolist() == [0, 1, 0] and b.type_names == ["KS", "AT"]
+    assert len(b.skipped) == 1
+    # label precedence without external alias: own alias, else ID (BGClib.py:1991-2002)
+    b2 = extract(col)
+    assert [r.type_key for r in b2.records] == ["KS", "AT", "ketoacyl-synt"]
+    # cbp_only honours CBPcontent
+    col2 = build_collection(spec, cbp=False)
+    assert len(extract(col2, cbp_only=True)) == 0 and len(extract(col2, cbp_only=False)) == 3
+    # domain type filter
+    assert len(extract(col, alias={"ketoacyl-synt": "KS"}, domain_types={"KS"})) == 2
+
+
+def test_extract_protein_units_and_strings(ks_records):
+    pc = FakeProteinCollection()
+    for r in ks_records:
+        pc.proteins[r["identifier"]] = FakeProtein(r["identifier"], r["sequence"])
+    b = extract(pc, unit="protein")
+    assert len(b) == 15 and b.sequences[0] == ks_records[0]["sequence"]
+    b2 = extract(["acd efg\n", "WWW"])
+    assert b2.sequences == ["ACDEFG", "WWW"]
+
+
+def test_resolve_matrix_and_concat():
+    assert (resolve_matrix("blosum62") == oracle.BLOSUM62).all()
+    with pytest.raises(ValueError):
+        resolve_matrix("PAM999")
+    bad = np.array(oracle.BLOSUM62, dtype=np.int64)
+    bad[0, 1] = 3
+    with pytest.raises(ValueError):
+        resolve_matrix(bad)
+    a, off = eng.concat_ascii(["AC", "D", "EFG"])
+    assert a.tobytes() == b"ACDEFG" and off.tolist() == [0, 2, 3, 6]
+
+
+def test_synth_is_deterministic_and_in_range():
+    a = synth.ks_like(300)
+    b = synth.ks_like(300)
+    assert (a.ascii == b.ascii).all() and (a.offsets == b.offsets).all()
+    L = a.lengths
+    assert L.min() >= 360 and L.max() <= 480 and abs(L.mean() - 420) < 10
+    assert set(a.ascii.tobytes().decode()) <= set(synth.AA20)
+    st = a.pair_stats()
+    assert st["pairs"] == 300 * 301 // 2
+    assert st["cells"] == sum(int(L[i]) * int(L[j]) for i in range(300) for j in range(i, 300))
+    m = synth.mixed_collection(20, 1, {"A": 1, "T/ACP": 2})
+    assert m.lengths.min() >= 70 and m.lengths.max() <= 600 and m.n_bgc == 20
+    # family structure: related members score far above unrelated background
+    seqs = synth.ks_like(120, family_size=60).sequences()
+    sc = oracle.all_pairs(seqs[:40])
+    assert np.triu(sc, 1).max() > 400
+
+
+@pytest.mark.parametrize("local", [True, False])
+def test_systolic_model_equals_oracle(local):
+    """The kernel's recurrence / boundary / capture logic, modelled in Python."""
+    rng = np.random.default_rng(42)
+    sub = oracle.BLOSUM62.astype(int).tolist()
+    for _ in range(40):
+        la, ls = int(rng.integers(1, 36)), int(rng.integers(1, 50))
+        q = rng.integers(0, 24, la).astype(np.uint8)
+        s = rng.integers(0, 24, ls).astype(np.uint8)
+        if rng.random() < 0.5:
+            s = np.concatenate([q, s])[:ls].astype(np.uint8)
+        for G, K in ((8, 5), (4, 9), (16, 3)):
+            if G * K < la:
+                continue
+            for o, e in ((-12, -1), (-4, -2)):
+                want = oracle.score(q, s, mode=0 if local else 1, open_gap=o, extend_gap=e)
+                assert systolic_score(q.tolist(), s.tolist(), sub, o, e, local, G, K) == want
