@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""ncu report -> compact per-launch metric table (CSV) for profiles/.
+usage: python profiles/summarize_ncu.py gpurun_out/prof.ncu-rep profiles/out.csv"""
+import csv
+import subprocess
+import sys
+
+KEEP = [
+    "Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers",
+    "launch__occupancy_limit_shared_mem", "gpu__time_duration.sum",
+    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.avg.per_cycle_active",
+    "sm__inst_executed.sum", "sm__inst_executed_pipe_alu.sum", "sm__inst_executed_pipe_fma.sum",
+    "sm__inst_executed_pipe_lsu.sum",
+    "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "smsp__warps_eligible.avg.per_cycle_active",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+    "sm__sass_inst_executed_op_shared_ld.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.max",
+]
+
+
+def main(rep, out):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True,
+                         check=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    cols = [i for i, h in enumerate(hdr) if h in KEEP]
+    with open(out, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["metric", "unit"] + [f"launch{k}" for k in range(len(data))])
+        for i in cols:
+            w.writerow([hdr[i], units[i]] + [r[i] for r in data])
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], sys.argv[2])
