@@ -31,7 +31,9 @@ UNITS = [("bgca_api.o", "bgca_api.cu", []),
          ("dpx_probe.o", "dpx_probe.cu", [])]
 for g in (8, 16, 32):
     for m in (0, 1):
-        UNITS.append((f"dp_g{g}_m{m}.o", "dp_inst.cu", [f"-DBGCA_INST_G={g}", f"-DBGCA_INST_MODE={m}"]))
+        for pr in (0, 1, 2):
+            UNITS.append((f"dp_g{g}_m{m}_p{pr}.o", "dp_inst.cu",
+                          [f"-DBGCA_INST_G={g}", f"-DBGCA_INST_MODE={m}", f"-DBGCA_INST_PRESET={pr}"]))
 
 
 def _sources_mtime() -> float:

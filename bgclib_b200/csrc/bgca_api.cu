@@ -490,6 +490,8 @@ static void fill_params(const bgca_engine *e, ScoreParams &p, int32_t *scores, i
     p.n_bgc = e->n_bgc;
     p.open = e->open;
     p.extend = e->extend;
+    p.open2 = ((uint32_t)e->open & 0xFFFFu) * 0x10001u;
+    p.ext2 = ((uint32_t)e->extend & 0xFFFFu) * 0x10001u;
     p.type_check = type_check;
     std::memcpy(p.sub, e->sub, NSYM * NSYM);
 }
@@ -563,9 +565,20 @@ int bgca_score(bgca_engine *e, int32_t *scores, int32_t *rowbest, int32_t *selfs
         cudaError_t err = cudaErrorInvalidValue;
         int grid = 0;
         const bool local = e->mode == BGCA_MODE_LOCAL;
-        if (G == 8) err = local ? launch_pair16_g8_m0(K, p, e->n_sm, st, &grid) : launch_pair16_g8_m1(K, p, e->n_sm, st, &grid);
-        else if (G == 16) err = local ? launch_pair16_g16_m0(K, p, e->n_sm, st, &grid) : launch_pair16_g16_m1(K, p, e->n_sm, st, &grid);
-        else if (G == 32) err = local ? launch_pair16_g32_m0(K, p, e->n_sm, st, &grid) : launch_pair16_g32_m1(K, p, e->n_sm, st, &grid);
+        // [G index][mode][gap preset]; preset 0 takes the gap scores at run time
+        static const Pair16Launcher table[3][2][3] = {
+            {{launch_pair16_g8_m0_p0, launch_pair16_g8_m0_p1, launch_pair16_g8_m0_p2},
+             {launch_pair16_g8_m1_p0, launch_pair16_g8_m1_p1, launch_pair16_g8_m1_p2}},
+            {{launch_pair16_g16_m0_p0, launch_pair16_g16_m0_p1, launch_pair16_g16_m0_p2},
+             {launch_pair16_g16_m1_p0, launch_pair16_g16_m1_p1, launch_pair16_g16_m1_p2}},
+            {{launch_pair16_g32_m0_p0, launch_pair16_g32_m0_p1, launch_pair16_g32_m0_p2},
+             {launch_pair16_g32_m1_p0, launch_pair16_g32_m1_p1, launch_pair16_g32_m1_p2}}};
+        const int gi = (G == 8) ? 0 : (G == 16) ? 1 : (G == 32) ? 2 : -1;
+        int preset = 0;
+        if (e->open == -12 && e->extend == -1) preset = 1;
+        else if (e->open == -11 && e->extend == -1) preset = 2;
+        if (std::getenv("BGCA_NO_PRESET")) preset = 0;   // tuning aid: force the run-time-gap kernels
+        if (gi >= 0) err = table[gi][local ? 0 : 1][preset](K, p, e->n_sm, st, &grid);
         if (err != cudaSuccess)
             return fail(BGCA_ERR_CUDA, std::string("DP kernel launch (G=") + std::to_string(G) + ",K=" +
                                            std::to_string(K) + "): " + cudaGetErrorString(err));

@@ -31,6 +31,7 @@ struct ScoreParams {
     int32_t n;
     int32_t n_bgc;
     int32_t open, extend;      // negative scores
+    uint32_t open2, ext2;      // the same, replicated in both 16-bit halves
     int32_t type_check;
     int8_t sub[NSYM * NSYM];
 };

@@ -1,21 +1,22 @@
-// Instantiations of the packed DP kernel for one (G, MODE); compiled six times
-// (G in {8,16,32} x MODE in {local, global}) so the build parallelises.
+// Instantiations of the packed DP kernel for one (G, MODE, PRESET); compiled 18
+// times (G in {8,16,32} x MODE in {local, global} x gap preset) so the build
+// parallelises.
 #include "gotoh_pair16.cuh"
 #include "launchers.h"
 #include "variants.h"
 
-#ifndef BGCA_INST_G
-#error "define BGCA_INST_G and BGCA_INST_MODE"
+#if !defined(BGCA_INST_G) || !defined(BGCA_INST_MODE) || !defined(BGCA_INST_PRESET)
+#error "define BGCA_INST_G, BGCA_INST_MODE and BGCA_INST_PRESET"
 #endif
 
 namespace bgca {
 
-template <int G, int K, int MODE>
+template <int G, int K, int MODE, int PRESET>
 static cudaError_t launch_one(const ScoreParams &p, int n_sm, cudaStream_t st, int *grid_out)
 {
     using Cfg = Pair16Cfg<G, K>;
     static int ctas_per_sm = 0;   // per instantiation, resolved on first use
-    auto kern = gotoh_pair16_kernel<G, K, MODE>;
+    auto kern = gotoh_pair16_kernel<G, K, MODE, PRESET>;
     if (ctas_per_sm == 0) {
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                Cfg::SMEM_BYTES);
@@ -32,17 +33,16 @@ static cudaError_t launch_one(const ScoreParams &p, int n_sm, cudaStream_t st, i
     return cudaGetLastError();
 }
 
-#define BGCA_CAT2(a, b, c, d) a##b##c##d
-#define BGCA_CAT(a, b, c, d) BGCA_CAT2(a, b, c, d)
+#define BGCA_CAT2(a, b, c, d, e, f) a##b##c##d##e##f
+#define BGCA_CAT(a, b, c, d, e, f) BGCA_CAT2(a, b, c, d, e, f)
 
-cudaError_t BGCA_CAT(launch_pair16_g, BGCA_INST_G, _m, BGCA_INST_MODE)(int K, const ScoreParams &p,
-                                                                      int n_sm, cudaStream_t st,
-                                                                      int *grid_out)
+cudaError_t BGCA_CAT(launch_pair16_g, BGCA_INST_G, _m, BGCA_INST_MODE, _p, BGCA_INST_PRESET)(
+    int K, const ScoreParams &p, int n_sm, cudaStream_t st, int *grid_out)
 {
     switch (K) {
 #define X(G, KK) \
     case KK:     \
-        return launch_one<BGCA_INST_G, KK, BGCA_INST_MODE>(p, n_sm, st, grid_out);
+        return launch_one<BGCA_INST_G, KK, BGCA_INST_MODE, BGCA_INST_PRESET>(p, n_sm, st, grid_out);
         BGCA_K_LIST(X, BGCA_INST_G)
 #undef X
         default:

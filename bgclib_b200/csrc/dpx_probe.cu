@@ -59,10 +59,10 @@ __global__ void __launch_bounds__(512) probe_cell_kernel(uint32_t ext2, uint32_t
                                                          uint32_t *sink, long long *cycles)
 {
     constexpr int K = 8;
-    uint32_t Hp[K], Eh[K], P[K];
+    uint32_t Ho[K], E[K], P[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        Hp[k] = 0; Eh[k] = 0;
+        Ho[k] = 0; E[k] = 0;
         P[k] = (seed * (threadIdx.x + 3 + k)) & 0x00070007u;
     }
     uint32_t best = 0, hin_prev = 0, h_in = seed & 0x000F000Fu, f_in = 0;
@@ -73,17 +73,18 @@ __global__ void __launch_bounds__(512) probe_cell_kernel(uint32_t ext2, uint32_t
         uint32_t diag = hin_prev;
         hin_prev = h_in;
         uint32_t up = h_in, F = f_in;
+        uint32_t h_prev = 0;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            Eh[k] = __viaddmax_s16x2(Eh[k], ext2, Hp[k]);
+            E[k] = __viaddmax_s16x2(E[k], ext2, Ho[k]);
             F = __viaddmax_s16x2(F, ext2, up);
-            const uint32_t u = __vmaxs2(Eh[k], F);
             const uint32_t tt = __vadd2(diag, P[k]);
-            const uint32_t h = __viaddmax_s16x2_relu(u, open2, tt);
-            diag = Hp[k];
-            Hp[k] = h;
-            if (k & 1) best = __vimax3_s16x2(best, up, h);
-            up = h;
+            const uint32_t h = __vimax3_s16x2_relu(tt, E[k], F);
+            diag = Ho[k];
+            up = __vadd2(h, open2);
+            Ho[k] = up;
+            if (k & 1) best = __vimax3_s16x2(best, h_prev, h);
+            h_prev = h;
         }
         h_in = up ^ (uint32_t)it;   // keep the next step dependent on this one
         f_in = F;
@@ -91,6 +92,89 @@ __global__ void __launch_bounds__(512) probe_cell_kernel(uint32_t ext2, uint32_t
     const long long t1 = clock64();
     if (best == 0x12345678u) sink[0] = best;
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+// Mixed-pipe throughput: half of the chains run op A, half op B, independent.
+// If A and B issue to different pipes the sum approaches 128 lane-ops/clk/SM.
+template <int A, int B>
+__global__ void __launch_bounds__(512) probe_mix_kernel(uint32_t a, uint32_t seed, uint32_t *sink,
+                                                        long long *cycles)
+{
+    uint32_t x[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) x[i] = seed * (threadIdx.x + 1) + i * 0x9E3779B9u;
+    __syncthreads();
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < PROBE_ITERS; ++it) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int i = 0; i < NCH; i += 2) {
+                x[i] = probe_op<A>(x[i], x[(i + 2) % NCH], a);
+                x[i + 1] = probe_op<B>(x[i + 1], x[(i + 3) % NCH], a);
+            }
+        }
+    }
+    const long long t1 = clock64();
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) acc ^= x[i];
+    if (acc == 0x12345678u) sink[0] = acc;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+// Dependent-chain latency: ONE warp per SM, one chain; cycles per op.
+// CHAIN 0: viaddmax -> viaddmax ...   1: vimax3 ...   2: vadd2 ...
+// CHAIN 3: the cell chain of the DP kernel: F=viaddmax(F,e,Ho); H=vimax3_relu(T,E,F); Ho=vadd2(H,o)
+template <int CHAIN>
+__global__ void __launch_bounds__(32) probe_latency_kernel(uint32_t a, uint32_t b, uint32_t seed,
+                                                           uint32_t *sink, long long *cycles)
+{
+    uint32_t x = seed * (threadIdx.x + 1), y = seed ^ 0x00050003u, z = seed & 0x00070007u;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < PROBE_ITERS; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            if (CHAIN == 0) x = __viaddmax_s16x2(x, a, b);
+            if (CHAIN == 1) x = __vimax3_s16x2(x, a, b);
+            if (CHAIN == 2) x = __vadd2(x, a);
+            if (CHAIN == 3) {
+                y = __viaddmax_s16x2(y, a, x);
+                const uint32_t h = __vimax3_s16x2_relu(z, b, y);
+                x = __vadd2(h, a);
+            }
+        }
+    }
+    const long long t1 = clock64();
+    if ((x ^ y) == 0x12345678u) sink[0] = x;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int CHAIN>
+static double run_latency(int n_sm, uint32_t *sink, long long *d_cycles, long long *h_cycles)
+{
+    probe_latency_kernel<CHAIN><<<n_sm, 32>>>(0xFFFFFFFFu, 0x00010002u, 99u, sink, d_cycles);
+    probe_latency_kernel<CHAIN><<<n_sm, 32>>>(0xFFFFFFFFu, 0x00010002u, 99u, sink, d_cycles);
+    if (cudaMemcpy(h_cycles, d_cycles, sizeof(long long) * n_sm, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return -1.0;
+    long long best = h_cycles[0];
+    for (int i = 1; i < n_sm; ++i) best = h_cycles[i] < best ? h_cycles[i] : best;
+    return (double)best / (8.0 * PROBE_ITERS);   // cycles per op (CHAIN 3: per 3-op cell)
+}
+
+template <int A, int B>
+static double run_mix(int n_sm, uint32_t *sink, long long *d_cycles, long long *h_cycles)
+{
+    const int grid = n_sm * 2;
+    probe_mix_kernel<A, B><<<grid, 512>>>(0x00030005u, 12345u, sink, d_cycles);
+    probe_mix_kernel<A, B><<<grid, 512>>>(0x00030005u, 12345u, sink, d_cycles);
+    if (cudaMemcpy(h_cycles, d_cycles, sizeof(long long) * grid, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return -1.0;
+    long long worst = 0;
+    for (int i = 0; i < grid; ++i) worst = h_cycles[i] > worst ? h_cycles[i] : worst;
+    return 1024.0 * NCH * 4.0 * PROBE_ITERS / (double)worst;
 }
 
 template <int OP>
@@ -119,7 +203,7 @@ int dpx_probe_run(int device, double *out, int n)
     if (cudaMalloc(&sink, 64) != cudaSuccess) return -1;
     if (cudaMalloc(&d_cycles, sizeof(long long) * grid) != cudaSuccess) return -1;
     long long *h_cycles = new long long[grid];
-    double r[10] = {0};
+    double r[20] = {0};
     r[0] = run_op<0>(n_sm, sink, d_cycles, h_cycles);
     r[1] = run_op<1>(n_sm, sink, d_cycles, h_cycles);
     r[2] = run_op<2>(n_sm, sink, d_cycles, h_cycles);
@@ -147,11 +231,19 @@ int dpx_probe_run(int device, double *out, int n)
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
     }
+    r[10] = run_mix<0, 3>(n_sm, sink, d_cycles, h_cycles);   // VIADDMNMX.S16x2 + VIADD.16x2
+    r[11] = run_mix<0, 5>(n_sm, sink, d_cycles, h_cycles);   // VIADDMNMX.S16x2 + IMAD
+    r[12] = run_mix<1, 3>(n_sm, sink, d_cycles, h_cycles);   // VIMNMX3.S16x2 + VIADD.16x2
+    r[13] = run_mix<3, 5>(n_sm, sink, d_cycles, h_cycles);   // VIADD.16x2 + IMAD
+    r[14] = run_latency<0>(n_sm, sink, d_cycles, h_cycles);
+    r[15] = run_latency<1>(n_sm, sink, d_cycles, h_cycles);
+    r[16] = run_latency<2>(n_sm, sink, d_cycles, h_cycles);
+    r[17] = run_latency<3>(n_sm, sink, d_cycles, h_cycles);
     delete[] h_cycles;
     cudaFree(sink);
     cudaFree(d_cycles);
     if (cudaGetLastError() != cudaSuccess) return -1;
-    for (int i = 0; i < n && i < 10; ++i) out[i] = r[i];
+    for (int i = 0; i < n && i < 20; ++i) out[i] = r[i];
     return 0;
 }
 

@@ -17,14 +17,15 @@
 // LDS.128 of a quarter-warp hit 8 distinct 16-byte bank groups whatever letter
 // each lane looks up (row stride is a multiple of 128 B).
 //
-// Per cell pair (hat form, E^ = E - open, F^ = F - open):
-//   E^ = viaddmax(E^, ext, Hleft)        VIADDMNMX.S16x2
-//   F^ = viaddmax(F^, ext, Hup)          VIADDMNMX.S16x2
-//   u  = max(E^, F^)                     VIMNMX.S16x2
-//   t  = Hdiag + s                       VIADD.16x2
-//   H  = max(u + open, t) [relu]         VIADDMNMX.S16x2[.RELU]
-//   best = max3(best, H_even, H_odd)     VIMNMX3.S16x2      (every 2nd cell, local)
-// = 5.5 ALU-pipe instructions per 2 cells (local), 5 (global).
+// Per cell pair ("Ho" form: the registers keep Ho = H + open, the profile holds
+// s - open, so the diagonal needs no second copy of H):
+//   E  = viaddmax(E, ext, Ho_left)       VIADDMNMX.S16x2        alu pipe
+//   F  = viaddmax(F, ext, Ho_up)         VIADDMNMX.S16x2        alu pipe
+//   t  = Ho_diag + (s - open)            VIADD.16x2             fma pipe (ncu: pipe_fma)
+//   H  = max3(t, E, F) [relu]            VIMNMX3.S16x2[.RELU]   alu pipe
+//   Ho = H + open                        VIADD.16x2             fma pipe
+//   best = max3(best, H_even, H_odd)     VIMNMX3.S16x2          alu pipe, every 2nd cell (local)
+// = 5.5 issue slots per 2 cells of which 3.5 on the alu pipe (local); 5 / 3 (global).
 #pragma once
 #include "common.cuh"
 
@@ -45,7 +46,18 @@ struct Pair16Cfg {
     static constexpr int MIN_CTAS = (K <= 8) ? 5 : (K <= 16) ? 4 : (K <= 24) ? 3 : 2;
 };
 
-template <int G, int K, int MODE>
+// Gap presets: with the gap scores known at compile time the DPX ops take them as
+// immediates, which saves one register-file read per op (the register file, not a
+// pipe, is what the mixed alu/fma stream saturates — see DESIGN.md "What bounds it").
+// PRESET 0 = run-time gap scores (any open <= extend <= 0).
+template <int PRESET> struct GapPreset { static constexpr int OPEN = 0, EXT = 0; };
+template <> struct GapPreset<1> { static constexpr int OPEN = -12, EXT = -1; };   // Biopython blastp preset
+template <> struct GapPreset<2> { static constexpr int OPEN = -11, EXT = -1; };   // BLAST "11/1" read as open+extend
+constexpr int NUM_GAP_PRESETS = 3;
+
+__host__ __device__ constexpr uint32_t cpack2(int v) { return ((uint32_t)v & 0xFFFFu) * 0x10001u; }
+
+template <int G, int K, int MODE, int PRESET>
 __global__ void __launch_bounds__(CTA_THREADS, (Pair16Cfg<G, K>::MIN_CTAS))
 gotoh_pair16_kernel(const ScoreParams p)
 {
@@ -67,7 +79,9 @@ gotoh_pair16_kernel(const ScoreParams p)
 
     for (int i = tid; i < NSYM * NSYM; i += CTA_THREADS) ssub[i] = p.sub[i];
 
-    const uint32_t ext2 = pack2(p.extend), open2 = pack2(p.open);
+    // (e,e) / (o,o): immediates under a preset, pre-packed kernel parameters otherwise
+    const uint32_t ext2 = PRESET ? cpack2(GapPreset<PRESET>::EXT) : p.ext2;
+    const uint32_t open2 = PRESET ? cpack2(GapPreset<PRESET>::OPEN) : p.open2;
 
     for (;;) {
         if (tid == 0) s_tile = atomicAdd(p.tile_counter, 1);
@@ -94,8 +108,9 @@ gotoh_pair16_kernel(const ScoreParams p)
             for (int idx = tid; idx < NSYM * LPAD; idx += CTA_THREADS) {
                 const int b = idx / LPAD, pos = idx - b * LPAD;
                 const int ca = qcodes[pos], cb = qcodes[LPAD + pos];
-                const int sa = (ca < NSYM) ? ssub[ca * NSYM + b] : 0;   // rows past the query: 0
-                const int sb = (cb < NSYM) ? ssub[cb * NSYM + b] : 0;
+                // profile word = score - open; rows past the query score 0
+                const int sa = ((ca < NSYM) ? ssub[ca * NSYM + b] : 0) - p.open;
+                const int sb = ((cb < NSYM) ? ssub[cb * NSYM + b] : 0) - p.open;
                 const int tt = pos / K, k = pos - tt * K;
                 pw[(((b * CH) + (k >> 2)) * G + tt) * 4 + (k & 3)] =
                     ((uint32_t)sa & 0xFFFFu) | ((uint32_t)sb << 16);
@@ -118,16 +133,16 @@ gotoh_pair16_kernel(const ScoreParams p)
                 for (int off = G; off < 32; off <<= 1) Lmax = max(Lmax, __shfl_xor_sync(FULL, Lmax, off));
             }
 
-            uint32_t Hp[K], Eh[K];
+            uint32_t Ho[K], E[K];     // Ho[k] = H[i0+k][j-1] + open,  E[k] = E[i0+k][j-1]
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                Hp[k] = LOCAL ? 0u : pack2(p.open + (i0 + k) * p.extend);
-                Eh[k] = LOCAL ? 0u : NEG16x2;
+                Ho[k] = LOCAL ? open2 : pack2(2 * p.open + (i0 + k) * p.extend);
+                E[k] = LOCAL ? 0u : NEG16x2;
             }
             uint32_t best = 0;
             uint32_t h_out = 0, f_out = 0;
-            // H[i0-1][j-1]: column boundary of the row above this lane
-            uint32_t hin_prev = (LOCAL || t == 0) ? 0u : pack2(p.open + (i0 - 1) * p.extend);
+            // Ho[i0-1][j-1]: column boundary of the row above this lane
+            uint32_t hin_prev = (LOCAL || t == 0) ? open2 : pack2(2 * p.open + (i0 - 1) * p.extend);
             uint32_t capA = 0, capB = 0;
             int j = -t;
             uint32_t c_next = ((unsigned)j < (unsigned)Ls) ? (uint32_t)__ldg(sp + j) : 0u;
@@ -138,8 +153,8 @@ gotoh_pair16_kernel(const ScoreParams p)
                 uint32_t f_in = __shfl_up_sync(FULL, f_out, 1, G);
                 const uint32_t c = c_next;
                 c_next = ((unsigned)(j + 1) < (unsigned)Ls) ? (uint32_t)__ldg(sp + j + 1) : 0u;
-                if (t == 0) {                       // top boundary row H[-1][j]
-                    h_in = LOCAL ? 0u : pack2(p.open + j * p.extend);
+                if (t == 0) {                       // top boundary row: Ho[-1][j], F[-1][j]
+                    h_in = LOCAL ? open2 : pack2(2 * p.open + j * p.extend);
                     f_in = LOCAL ? 0u : NEG16x2;
                 }
                 if ((unsigned)j < (unsigned)Ls) {
@@ -151,24 +166,30 @@ gotoh_pair16_kernel(const ScoreParams p)
                         P[ch * 4 + 0] = v.x; P[ch * 4 + 1] = v.y;
                         P[ch * 4 + 2] = v.z; P[ch * 4 + 3] = v.w;
                     }
-                    uint32_t diag = hin_prev;
+                    // phase 1 — independent adds (fma pipe): T[k] = H_diag + s, in place in P
+                    P[0] = __vadd2(hin_prev, P[0]);
+#pragma unroll
+                    for (int k = 1; k < K; ++k) P[k] = __vadd2(Ho[k - 1], P[k]);
                     hin_prev = h_in;
+                    // phase 2 — the dependent chain down this lane's rows
                     uint32_t up = h_in, F = f_in;
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
-                        Eh[k] = __viaddmax_s16x2(Eh[k], ext2, Hp[k]);
+                        E[k] = __viaddmax_s16x2(E[k], ext2, Ho[k]);
                         F = __viaddmax_s16x2(F, ext2, up);
-                        const uint32_t u = __vmaxs2(Eh[k], F);
-                        const uint32_t tt = __vadd2(diag, P[k]);
-                        const uint32_t h = LOCAL ? __viaddmax_s16x2_relu(u, open2, tt)
-                                                 : __viaddmax_s16x2(u, open2, tt);
-                        diag = Hp[k];
-                        Hp[k] = h;
+                        const uint32_t h = LOCAL ? __vimax3_s16x2_relu(P[k], E[k], F)
+                                                 : __vimax3_s16x2(P[k], E[k], F);
+                        up = __vadd2(h, open2);
+                        Ho[k] = up;
                         if (LOCAL) {
-                            if (k & 1) best = __vimax3_s16x2(best, up, h);   // up = H of row k-1
-                            else if (k == K - 1) best = __vmaxs2(best, h);
+                            // The best cell of a local alignment is always entered by a
+                            // substitution (E/F only ever lower an earlier H), so tracking
+                            // max(H_diag + s) is exact — and gives the sum a second reader,
+                            // which keeps ptxas from folding the add into a VIADDMNMX on the
+                            // alu pipe.
+                            if (k & 1) best = __vimax3_s16x2(best, P[k - 1], P[k]);
+                            else if (k == K - 1) best = __vmaxs2(best, P[k]);
                         }
-                        up = h;
                     }
                     h_out = up;
                     f_out = F;
@@ -176,8 +197,8 @@ gotoh_pair16_kernel(const ScoreParams p)
                         if (j == Ls - 1) {          // last column: pick H[L-1][Ls-1] of each half
 #pragma unroll
                             for (int k = 0; k < K; ++k) {
-                                if (i0 + k == La - 1) capA = Hp[k];
-                                if (i0 + k == Lb - 1) capB = Hp[k];
+                                if (i0 + k == La - 1) capA = Ho[k];
+                                if (i0 + k == Lb - 1) capB = Ho[k];
                             }
                         }
                     }
@@ -194,8 +215,8 @@ gotoh_pair16_kernel(const ScoreParams p)
             } else {
                 const uint32_t a = __shfl_sync(FULL, capA, (La - 1) / K, G);
                 const uint32_t b = __shfl_sync(FULL, capB, (Lb > 0 ? Lb - 1 : 0) / K, G);
-                ra = (int32_t)(int16_t)(a & 0xFFFFu);
-                rb = (int32_t)(int16_t)(b >> 16);
+                ra = (int32_t)(int16_t)(a & 0xFFFFu) - p.open;      // captured Ho = H + open
+                rb = (int32_t)(int16_t)(b >> 16) - p.open;
             }
             if (t == 0 && valid) {
                 emit_pair(p, qa, s, ra);

@@ -4,15 +4,18 @@
 
 namespace bgca {
 
-#define BGCA_DECL_LAUNCH(G, M)                                                               \
-    cudaError_t launch_pair16_g##G##_m##M(int K, const ScoreParams &p, int n_sm, cudaStream_t st, \
-                                          int *grid_out);
-BGCA_DECL_LAUNCH(8, 0)
-BGCA_DECL_LAUNCH(8, 1)
-BGCA_DECL_LAUNCH(16, 0)
-BGCA_DECL_LAUNCH(16, 1)
-BGCA_DECL_LAUNCH(32, 0)
-BGCA_DECL_LAUNCH(32, 1)
+using Pair16Launcher = cudaError_t (*)(int K, const ScoreParams &p, int n_sm, cudaStream_t st,
+                                       int *grid_out);
+#define BGCA_DECL_LAUNCH(G, M, P) \
+    cudaError_t launch_pair16_g##G##_m##M##_p##P(int K, const ScoreParams &p, int n_sm, cudaStream_t st, int *grid_out);
+#define BGCA_DECL_LAUNCH_GM(G, M) BGCA_DECL_LAUNCH(G, M, 0) BGCA_DECL_LAUNCH(G, M, 1) BGCA_DECL_LAUNCH(G, M, 2)
+BGCA_DECL_LAUNCH_GM(8, 0)
+BGCA_DECL_LAUNCH_GM(8, 1)
+BGCA_DECL_LAUNCH_GM(16, 0)
+BGCA_DECL_LAUNCH_GM(16, 1)
+BGCA_DECL_LAUNCH_GM(32, 0)
+BGCA_DECL_LAUNCH_GM(32, 1)
+#undef BGCA_DECL_LAUNCH_GM
 #undef BGCA_DECL_LAUNCH
 
 cudaError_t launch_s32(int mode, const ScoreParams &p, const int32_t *pq, const int32_t *ps,

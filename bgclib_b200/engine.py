@@ -306,8 +306,10 @@ class Engine:
 
 def dpx_probe(device: int = 0) -> dict:
     lib = load_library()
-    out = (ctypes.c_double * 10)()
-    _check(lib.bgca_dpx_probe(device, out, 10))
+    out = (ctypes.c_double * 20)()
+    _check(lib.bgca_dpx_probe(device, out, 20))
     names = ["viaddmnmx_s16x2", "vimnmx3_s16x2", "vimnmx_s16x2", "viadd_16x2", "iadd3", "imad", "prmt",
-             "viaddmnmx_s32", "cell_mix_s16x2", "sm_mhz"]
+             "viaddmnmx_s32", "cell_mix_s16x2", "sm_mhz",
+             "mix_viaddmnmx+viadd16x2", "mix_viaddmnmx+imad", "mix_vimnmx3+viadd16x2", "mix_viadd16x2+imad",
+             "lat_viaddmnmx_cyc", "lat_vimnmx3_cyc", "lat_viadd16x2_cyc", "lat_cell_chain_cyc"]
     return {k: float(v) for k, v in zip(names, out)}

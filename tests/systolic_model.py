@@ -1,7 +1,8 @@
 """Pure-Python model of the data flow of gotoh_pair16_kernel (one alignment group,
 one half of the packed registers): lane t owns query rows [t*K, (t+1)*K), at step
 tau it sweeps subject column j = tau - t, H/F^ of its bottom row move to lane t+1
-one step later.  Hat form: E^ = E - open, F^ = F - open.  Used by the CPU tests to
+one step later.  "Ho" form: registers keep Ho = H + open and the profile holds
+s - open, as in the kernel.  Used by the CPU tests to
 check the kernel's recurrence, boundaries and capture logic against the oracle
 without a GPU; it mirrors bgclib_b200/csrc/gotoh_pair16.cuh statement by statement.
 """
@@ -11,9 +12,9 @@ NEG = -30000
 def systolic_score(q, s, sub, open_, ext, local, G, K):
     La, Ls = len(q), len(s)
     assert G * K >= La
-    Hp = [[0 if local else open_ + (t * K + k) * ext for k in range(K)] for t in range(G)]
-    Eh = [[0 if local else NEG for _ in range(K)] for t in range(G)]
-    hin_prev = [0 if (local or t == 0) else open_ + (t * K - 1) * ext for t in range(G)]
+    Ho = [[open_ if local else 2 * open_ + (t * K + k) * ext for k in range(K)] for t in range(G)]
+    E = [[0 if local else NEG for _ in range(K)] for t in range(G)]
+    hin_prev = [open_ if (local or t == 0) else 2 * open_ + (t * K - 1) * ext for t in range(G)]
     h_out = [0] * G
     f_out = [0] * G
     best = 0
@@ -26,7 +27,7 @@ def systolic_score(q, s, sub, open_, ext, local, G, K):
             j = tau - t
             h_in, f_in = h_sh[t], f_sh[t]
             if t == 0:
-                h_in = 0 if local else open_ + j * ext
+                h_in = open_ if local else 2 * open_ + j * ext
                 f_in = 0 if local else NEG
             if 0 <= j < Ls:
                 c = s[j]
@@ -35,21 +36,20 @@ def systolic_score(q, s, sub, open_, ext, local, G, K):
                 up, F = h_in, f_in
                 for k in range(K):
                     i = t * K + k
-                    sc = sub[q[i]][c] if i < La else 0
-                    Eh[t][k] = max(Eh[t][k] + ext, Hp[t][k])
+                    prof = (sub[q[i]][c] if i < La else 0) - open_
+                    E[t][k] = max(E[t][k] + ext, Ho[t][k])
                     F = max(F + ext, up)
-                    u = max(Eh[t][k], F)
-                    h = max(u + open_, diag + sc)
+                    h = max(diag + prof, E[t][k], F)
                     if local:
                         h = max(h, 0)
                         best = max(best, h)
-                    diag = Hp[t][k]
-                    Hp[t][k] = h
-                    up = h
+                    diag = Ho[t][k]
+                    up = h + open_
+                    Ho[t][k] = up
                 new_h[t], new_f[t] = up, F
                 if not local and j == Ls - 1:
                     for k in range(K):
                         if t * K + k == La - 1:
-                            cap = Hp[t][k]
+                            cap = Ho[t][k] - open_
         h_out, f_out = new_h, new_f
     return best if local else cap
