@@ -40,6 +40,8 @@ const VariantDesc kVariants[] = {
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr int kMaxPackedRows = 32 * 32;   // largest G*K
+constexpr int kSubjectsPerGroup = 16;
+constexpr uint64_t kPackedHeader = 64;    // bytes of TOK_IDLE (25) in front of the first sequence
 
 // Relative issue cost of sweeping one subject of length ~Lq with variant (G,K):
 // (steps) x (instructions per step) x (share of the warp one alignment uses).
@@ -115,10 +117,13 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, int32_t n, int sam
             int variant = pick_variant(Lq);
             const int G = variant >> 8;
             const int S = te - qa;
-            // subjects per tile: ~16 per alignment group of the CTA, split evenly
-            const int s_max = variant ? (CTA_THREADS / G) * 16 : 256;
+            // subjects per tile: ~kSubjectsPerGroup per alignment group (= subject stream) of
+            // the CTA, split evenly over the row and rounded up to a whole number per group
+            const int ngroups = variant ? CTA_THREADS / G : 16;
+            const int s_max = ngroups * kSubjectsPerGroup;
             const int nchunks = (S + s_max - 1) / s_max;
-            const int chunk = (S + nchunks - 1) / nchunks;
+            int chunk = (S + nchunks - 1) / nchunks;
+            chunk = (chunk + ngroups - 1) / ngroups * ngroups;
             for (int s0 = qa; s0 < te; s0 += chunk) {
                 const int s1 = std::min(te, s0 + chunk);
                 bgca_tile T{};
@@ -347,7 +352,7 @@ int bgca_pack(bgca_engine *e, const uint8_t *ascii, const int64_t *offsets, int3
     e->has_bgc = bgc_of_seq != nullptr;
     e->len.resize(n); e->type.assign(n, 0); e->bgc.assign(n, 0); e->seq_off.resize(n);
     e->inv_order.resize(n);
-    uint64_t off = 0;
+    uint64_t off = kPackedHeader;   // header of idle tokens (see gotoh_pair16.cuh)
     for (int r = 0; r < n; ++r) {
         const int o = e->order[r];
         e->inv_order[o] = r;
@@ -355,7 +360,7 @@ int bgca_pack(bgca_engine *e, const uint8_t *ascii, const int64_t *offsets, int3
         if (type_of_seq) e->type[r] = type_of_seq[o];
         if (bgc_of_seq) e->bgc[r] = bgc_of_seq[o];
         e->seq_off[r] = (uint32_t)off;
-        off += (uint64_t)((len_orig[o] + 15) & ~15);
+        off += (uint64_t)((len_orig[o] + 1 + 15) & ~15);   // >= 1 pad byte = end-of-subject token
         if (off > 0xFFFFFFF0ull) return fail(BGCA_ERR_RANGE, "bgca_pack: packed batch exceeds 4 GiB");
     }
     e->packed_bytes = (int64_t)off;
@@ -400,6 +405,8 @@ int bgca_pack(bgca_engine *e, const uint8_t *ascii, const int64_t *offsets, int3
     if (!e->bgc_doms.empty())
         CUDA_TRY(cudaMemcpyAsync(e->d_bgc_doms.p, e->bgc_doms.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(e->d_err.p, 0xFF, sizeof(unsigned long long), st));
+    CUDA_TRY(cudaMemsetAsync(e->d_codes.p, 25, kPackedHeader, st));
+    CUDA_TRY(cudaMemsetAsync(e->d_codes.p + off, BGCA_PAD_CODE, 16, st));
     CUDA_TRY(launch_pack(d_src, e->d_offsets_orig.p, e->d_order.p, e->d_seq_off.p, e->d_len.p, n,
                          e->d_codes.p, e->d_err.p, st));
     unsigned long long err = 0;

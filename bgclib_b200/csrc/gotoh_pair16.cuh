@@ -3,47 +3,79 @@
 // Layout of the work.  A tile is a *query pair* (qa, qb) against a run of
 // subjects.  The two queries live in the two 16-bit halves of every register,
 // so each DPX instruction advances two alignments that read the same subject
-// residue.  A group of G lanes sweeps one subject systolically: lane t owns
-// query rows [t*K, (t+1)*K) (H and E^ kept in registers for both queries), at
-// step tau it processes subject column j = tau - t; the bottom H / F^ of a
-// lane travel to lane t+1 with __shfl_up_sync.  G = 32 is the warp-cooperative
-// ("intra-sequence") form for long domains, G = 8/16 runs 4/2 subjects per
-// warp for short ones ("inter-sequence" in the limit).
+// residue.  A group of G lanes sweeps subjects systolically: lane t owns query
+// rows [t*K, (t+1)*K) (Ho = H + open and E kept in registers for both queries),
+// at every step it consumes one token of the group's subject stream, lagging
+// lane t-1 by one step; the bottom Ho / F of a lane travel to lane t+1 with
+// __shfl_up_sync.  G = 32 is the warp-cooperative ("intra-sequence") form for
+// long domains, G = 8/16 runs 4/2 streams per warp for short ones
+// ("inter-sequence" in the limit).
+//
+// Streaming.  A group does not drain its pipeline between subjects: its
+// subjects (s_begin + gid, + NGROUPS, ...) are consumed back to back as ONE token
+// stream — residues (< 24), then the pad byte the packer always leaves behind a
+// sequence (24 = "boundary"), then the next subject.  At a boundary token a lane
+// posts its best, the last lane collects and emits the two scores, state is
+// reset; lanes that have not started / have finished see IDLE tokens (25).
+// Boundary and idle handling sit on a cold path, so the hot loop carries no
+// per-step bounds checks and the G-1 step wind-up is paid once per tile, not
+// once per subject.
 //
 // The substitution scores come from a query-PAIR profile in shared memory:
 // prof[b][chunk][lane][4] holds, for subject letter b and query row i, the
-// word (sub[qa_i][b] | sub[qb_i][b] << 16) — already in s16x2 form, so the inner
-// loop needs no unpack/permute.  The [chunk][lane] interleave makes every
-// LDS.128 of a quarter-warp hit 8 distinct 16-byte bank groups whatever letter
-// each lane looks up (row stride is a multiple of 128 B).
+// word ((sub[qa_i][b]-open) | (sub[qb_i][b]-open) << 16) — already in s16x2 form,
+// so the inner loop needs no unpack/permute.  The [chunk][lane] interleave makes
+// every LDS.128 of a quarter-warp hit 8 distinct 16-byte bank groups whatever
+// letter each lane looks up (row stride is a multiple of 128 B).
 //
-// Per cell pair ("Ho" form: the registers keep Ho = H + open, the profile holds
-// s - open, so the diagonal needs no second copy of H):
-//   E  = viaddmax(E, ext, Ho_left)       VIADDMNMX.S16x2        alu pipe
-//   F  = viaddmax(F, ext, Ho_up)         VIADDMNMX.S16x2        alu pipe
-//   t  = Ho_diag + (s - open)            VIADD.16x2             fma pipe (ncu: pipe_fma)
-//   H  = max3(t, E, F) [relu]            VIMNMX3.S16x2[.RELU]   alu pipe
-//   Ho = H + open                        VIADD.16x2             fma pipe
+// Per cell pair ("next-T" form).  The per-row state is not H but what the NEXT
+// column needs from it: Tn[k] = Ho[k-1] + (s_next - open) (the diagonal term,
+// built with the profile row of the NEXT token, which is prefetched two steps
+// ahead) and E[k] already advanced to the next column.  Every state update is
+// then in place — no register copies, no saved diagonal:
+//   F   = viaddmax(F, ext, Ho_up)        VIADDMNMX.S16x2        alu pipe
+//   H   = max3(Tn[k], E[k], F) [relu]    VIMNMX3.S16x2[.RELU]   alu pipe
+//   Tn[k] = Ho_up + Pnext[k]             VIADD.16x2             fma pipe (ncu: pipe_fma)
+//   Ho  = H + open                       VIADD.16x2             fma pipe
+//   E[k] = viaddmax(E[k], ext, Ho)       VIADDMNMX.S16x2        alu pipe
 //   best = max3(best, H_even, H_odd)     VIMNMX3.S16x2          alu pipe, every 2nd cell (local)
 // = 5.5 issue slots per 2 cells of which 3.5 on the alu pipe (local); 5 / 3 (global).
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace bgca {
 
 constexpr uint32_t NEG16x2 = 0x8AD08AD0u;  // (-30000, -30000): "-inf" that survives +open/+extend
+constexpr uint32_t TOK_BOUNDARY = BGCA_PAD_CODE;   // 24: the pad byte behind every packed sequence
+constexpr uint32_t TOK_IDLE = 25;                  // fills the 64-byte header of the packed batch
 
 __device__ __forceinline__ uint32_t pack2(int v) { return ((uint32_t)v & 0xFFFFu) * 0x10001u; }
+__host__ __device__ constexpr uint32_t cpack2(int v) { return ((uint32_t)v & 0xFFFFu) * 0x10001u; }
+
+constexpr int PROF_ROWS = NSYM + 2;   // 24 residues + the two token rows (never scored, must be loadable)
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
 
 template <int G, int K>
 struct Pair16Cfg {
     static constexpr int CH = (K + 3) / 4;          // 16-byte chunks per lane per letter
     static constexpr int LPAD = G * K;              // query rows covered in one pass
-    static constexpr int ROW_U4 = CH * G;           // uint4 per profile row
-    static constexpr int PROF_BYTES = NSYM * ROW_U4 * 16;
-    static constexpr int SMEM_BYTES = PROF_BYTES + 2 * LPAD + NSYM * NSYM + 16;
-    // registers: 2K state + 4CH profile + ~24 -> pick CTAs/SM so ptxas has room
-    static constexpr int MIN_CTAS = (K <= 8) ? 5 : (K <= 16) ? 4 : (K <= 24) ? 3 : 2;
+    static constexpr int ROW_BYTES = CH * G * 16;   // one profile row (multiple of 128 B)
+    static constexpr int NGROUPS = CTA_THREADS / G; // alignment groups (subject streams) per CTA
+    static constexpr int PROF_BYTES = PROF_ROWS * ROW_BYTES;
+    static constexpr int BEST_BYTES = NGROUPS * 32 * 2 * 4;   // per group: ring of 32 (lo, hi) slots
+    static constexpr int SMEM_BYTES = PROF_BYTES + BEST_BYTES + 2 * LPAD + NSYM * NSYM + 16;
+    // registers: 2K state + 4CH profile + ~24 -> pick CTAs/SM so ptxas has room.  Global mode
+    // carries a second (final-column) copy of the column pass and needs a few more.
+    static constexpr int MIN_CTAS_LOCAL = (K <= 8) ? 5 : (K <= 14) ? 4 : (K <= 18) ? 3 : 2;
+    static constexpr int MIN_CTAS_GLOBAL = (K <= 8) ? 4 : (K <= 16) ? 3 : (K <= 18) ? 2 : 1;
 };
 
 // Gap presets: with the gap scores known at compile time the DPX ops take them as
@@ -55,33 +87,39 @@ template <> struct GapPreset<1> { static constexpr int OPEN = -12, EXT = -1; }; 
 template <> struct GapPreset<2> { static constexpr int OPEN = -11, EXT = -1; };   // BLAST "11/1" read as open+extend
 constexpr int NUM_GAP_PRESETS = 3;
 
-__host__ __device__ constexpr uint32_t cpack2(int v) { return ((uint32_t)v & 0xFFFFu) * 0x10001u; }
-
 template <int G, int K, int MODE, int PRESET>
-__global__ void __launch_bounds__(CTA_THREADS, (Pair16Cfg<G, K>::MIN_CTAS))
+__global__ void __launch_bounds__(CTA_THREADS, (MODE == BGCA_MODE_LOCAL ? Pair16Cfg<G, K>::MIN_CTAS_LOCAL
+                                                                         : Pair16Cfg<G, K>::MIN_CTAS_GLOBAL))
 gotoh_pair16_kernel(const ScoreParams p)
 {
     using Cfg = Pair16Cfg<G, K>;
-    constexpr int CH = Cfg::CH, LPAD = Cfg::LPAD;
+    constexpr int CH = Cfg::CH, LPAD = Cfg::LPAD, NGROUPS = Cfg::NGROUPS;
     constexpr bool LOCAL = (MODE == BGCA_MODE_LOCAL);
     constexpr unsigned FULL = 0xFFFFFFFFu;
 
     extern __shared__ uint4 smem_u4[];
-    uint4 *prof = smem_u4;                                            // [NSYM][CH][G]
-    uint8_t *qcodes = reinterpret_cast<uint8_t *>(smem_u4) + Cfg::PROF_BYTES;  // [2][LPAD]
+    uint4 *prof = smem_u4;                                                    // [PROF_ROWS][CH][G]
+    int *sbest = reinterpret_cast<int *>(reinterpret_cast<uint8_t *>(smem_u4) + Cfg::PROF_BYTES);
+    uint8_t *qcodes = reinterpret_cast<uint8_t *>(sbest) + Cfg::BEST_BYTES;   // [2][LPAD]
     int8_t *ssub = reinterpret_cast<int8_t *>(qcodes + 2 * LPAD);
     __shared__ int s_tile;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int t = lane % G;                 // lane within the alignment group
-    constexpr int NGROUPS = CTA_THREADS / G;
+    const int gid = tid / G;                // group (= subject stream) within the CTA
+    const int i0 = t * K;                   // first query row of this lane
 
     for (int i = tid; i < NSYM * NSYM; i += CTA_THREADS) ssub[i] = p.sub[i];
+    for (int i = tid; i < Cfg::BEST_BYTES / 4; i += CTA_THREADS) sbest[i] = 0;
 
     // (e,e) / (o,o): immediates under a preset, pre-packed kernel parameters otherwise
     const uint32_t ext2 = PRESET ? cpack2(GapPreset<PRESET>::EXT) : p.ext2;
     const uint32_t open2 = PRESET ? cpack2(GapPreset<PRESET>::OPEN) : p.open2;
+    const uint8_t *const idle_ptr = p.codes;            // header of the packed batch: TOK_IDLE bytes
+    int *const my_best = sbest + gid * 64;
+    // this lane's 16-byte column of the profile, as a 32-bit shared-window address
+    const uint32_t prof_lane = (uint32_t)__cvta_generic_to_shared(prof) + (uint32_t)t * 16u;
 
     for (;;) {
         if (tid == 0) s_tile = atomicAdd(p.tile_counter, 1);
@@ -105,12 +143,12 @@ gotoh_pair16_kernel(const ScoreParams p)
         __syncthreads();
         {
             uint32_t *pw = reinterpret_cast<uint32_t *>(prof);
-            for (int idx = tid; idx < NSYM * LPAD; idx += CTA_THREADS) {
+            for (int idx = tid; idx < PROF_ROWS * LPAD; idx += CTA_THREADS) {
                 const int b = idx / LPAD, pos = idx - b * LPAD;
                 const int ca = qcodes[pos], cb = qcodes[LPAD + pos];
-                // profile word = score - open; rows past the query score 0
-                const int sa = ((ca < NSYM) ? ssub[ca * NSYM + b] : 0) - p.open;
-                const int sb = ((cb < NSYM) ? ssub[cb * NSYM + b] : 0) - p.open;
+                // profile word = score - open; rows past the query (and the token rows) score 0
+                const int sa = ((ca < NSYM && b < NSYM) ? ssub[ca * NSYM + b] : 0) - p.open;
+                const int sb = ((cb < NSYM && b < NSYM) ? ssub[cb * NSYM + b] : 0) - p.open;
                 const int tt = pos / K, k = pos - tt * K;
                 pw[(((b * CH) + (k >> 2)) * G + tt) * 4 + (k & 3)] =
                     ((uint32_t)sa & 0xFFFFu) | ((uint32_t)sb << 16);
@@ -118,110 +156,160 @@ gotoh_pair16_kernel(const ScoreParams p)
         }
         __syncthreads();
 
-        // column-boundary values of this lane's rows (H[i][-1]); local: all 0
-        const int i0 = t * K;
-
-        // ---- subjects of this tile, NGROUPS at a time (warp-uniform trip count) --
-        for (int sbase = T.s_begin + (tid >> 5) * (32 / G); sbase < T.s_end; sbase += NGROUPS) {
-            const int s = sbase + (lane / G);
-            const bool valid = s < T.s_end;
-            const int Ls = valid ? p.seq_len[s] : 0;
-            const uint8_t *sp = p.codes + (valid ? p.seq_off[s] : 0u);
-            int Lmax = Ls;
-            if (G < 32) {
+        // ---- this group's subject stream ------------------------------------------
+        const int s_first = T.s_begin + gid;
+        const int n_g = (s_first < T.s_end) ? (T.s_end - s_first + NGROUPS - 1) / NGROUPS : 0;
+        int nsteps = 0;
+        for (int o = t; o < n_g; o += G) nsteps += p.seq_len[s_first + o * NGROUPS] + 1;
 #pragma unroll
-                for (int off = G; off < 32; off <<= 1) Lmax = max(Lmax, __shfl_xor_sync(FULL, Lmax, off));
-            }
+        for (int off = G / 2; off > 0; off >>= 1) nsteps += __shfl_xor_sync(FULL, nsteps, off);
+        nsteps = (n_g > 0) ? nsteps + G - 1 : 0;
+        if (G < 32) {
+#pragma unroll
+            for (int off = G; off < 32; off <<= 1) nsteps = max(nsteps, __shfl_xor_sync(FULL, nsteps, off));
+        }
 
-            uint32_t Ho[K], E[K];     // Ho[k] = H[i0+k][j-1] + open,  E[k] = E[i0+k][j-1]
+        // ---- lane state ------------------------------------------------------------
+        // Tn[k] = Ho[i0+k-1][j-1] + (sub(q_{i0+k}, residue j) - open)   diagonal term of the NEXT cell
+        // E[k]  = E[i0+k][j]                                            already advanced to column j
+        uint32_t Tn[K], E[K];
+        uint32_t capA = 0, capB = 0;    // global mode: Ho[La-1][last column] / Ho[Lb-1][last column]
+        uint32_t best = 0;
+        uint32_t h_out = 0, f_out = 0;
+        uint32_t top_h = LOCAL ? open2 : pack2(2 * p.open);     // lane 0: Ho[-1][j]
+        // column boundary (j = -1) of the row above this lane: Ho[i0-1][-1]
+        const uint32_t hin0 = (LOCAL || t == 0) ? open2 : pack2(2 * p.open + (i0 - 1) * p.extend);
+
+        // start of a subject whose first residue is c0: state for column 0
+        auto begin_subject = [&](uint32_t c0) {
+            const uint32_t a = prof_lane + c0 * (uint32_t)Cfg::ROW_BYTES;
+            uint32_t P[CH * 4];
+#pragma unroll
+            for (int ch = 0; ch < CH; ++ch) {
+                const uint4 v = lds128(a + ch * (G * 16));
+                P[ch * 4 + 0] = v.x; P[ch * 4 + 1] = v.y; P[ch * 4 + 2] = v.z; P[ch * 4 + 3] = v.w;
+            }
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                Ho[k] = LOCAL ? open2 : pack2(2 * p.open + (i0 + k) * p.extend);
-                E[k] = LOCAL ? 0u : NEG16x2;
+                const uint32_t above = (k == 0) ? hin0
+                                                : (LOCAL ? open2 : pack2(2 * p.open + (i0 + k - 1) * p.extend));
+                Tn[k] = __vadd2(above, P[k]);
+                // E advanced to column 0 = max(-inf + ext, Ho[i0+k][-1]); local: any value <= 0 is inert
+                E[k] = LOCAL ? 0u : pack2(2 * p.open + (i0 + k) * p.extend);
             }
-            uint32_t best = 0;
-            uint32_t h_out = 0, f_out = 0;
-            // Ho[i0-1][j-1]: column boundary of the row above this lane
-            uint32_t hin_prev = (LOCAL || t == 0) ? open2 : pack2(2 * p.open + (i0 - 1) * p.extend);
-            uint32_t capA = 0, capB = 0;
-            int j = -t;
-            uint32_t c_next = ((unsigned)j < (unsigned)Ls) ? (uint32_t)__ldg(sp + j) : 0u;
+            best = 0;
+            top_h = LOCAL ? open2 : pack2(2 * p.open);
+        };
 
-            const int nsteps = Lmax + G - 1;
-            for (int tau = 0; tau < nsteps; ++tau, ++j) {
-                uint32_t h_in = __shfl_up_sync(FULL, h_out, 1, G);
-                uint32_t f_in = __shfl_up_sync(FULL, f_out, 1, G);
-                const uint32_t c = c_next;
-                c_next = ((unsigned)(j + 1) < (unsigned)Ls) ? (uint32_t)__ldg(sp + j + 1) : 0u;
-                if (t == 0) {                       // top boundary row: Ho[-1][j], F[-1][j]
-                    h_in = LOCAL ? open2 : pack2(2 * p.open + j * p.extend);
-                    f_in = LOCAL ? 0u : NEG16x2;
-                }
-                if ((unsigned)j < (unsigned)Ls) {
-                    const uint4 *prow = prof + c * (CH * G) + t;
+        int ord = 0;                                            // subjects this lane has finished
+        int wait = (n_g > 0) ? t : 0;                           // idle steps before this lane starts
+        const uint8_t *ptr = idle_ptr;                          // address of the token two steps ahead
+        uint32_t inc = 0;
+        uint32_t c = TOK_IDLE, c1 = TOK_IDLE;                   // token of this step / of the next step
+#pragma unroll
+        for (int k = 0; k < K; ++k) { Tn[k] = 0; E[k] = 0; }
+        if (n_g > 0 && t == 0) {
+            const uint8_t *s0 = p.codes + p.seq_off[s_first];
+            c = __ldg(s0);
+            c1 = __ldg(s0 + 1);
+            ptr = s0 + 2;
+            inc = 1;
+            begin_subject(c);
+        }
+
+        for (int tau = 0; tau < nsteps; ++tau) {
+            uint32_t h_in = __shfl_up_sync(FULL, h_out, 1, G);
+            uint32_t f_in = __shfl_up_sync(FULL, f_out, 1, G);
+            uint32_t c2 = __ldg(ptr);
+            ptr += inc;
+            if (t == 0) {                       // top boundary row: Ho[-1][j], F[-1][j]
+                h_in = top_h;
+                f_in = LOCAL ? 0u : NEG16x2;
+            }
+            if (c < TOK_BOUNDARY) {
+                // ================= hot path: one residue of the current subject ========
+                // LAST (global mode only): this is the subject's final column — the lanes that
+                // own rows La-1 / Lb-1 keep their Ho for the boundary step.
+                auto column = [&](auto last_tag) {
+                    constexpr bool LAST = decltype(last_tag)::value;
+                    const uint32_t a = prof_lane + c1 * (uint32_t)Cfg::ROW_BYTES;   // row of the NEXT token
                     uint32_t P[CH * 4];
 #pragma unroll
                     for (int ch = 0; ch < CH; ++ch) {
-                        const uint4 v = prow[ch * G];
-                        P[ch * 4 + 0] = v.x; P[ch * 4 + 1] = v.y;
-                        P[ch * 4 + 2] = v.z; P[ch * 4 + 3] = v.w;
+                        const uint4 v = lds128(a + ch * (G * 16));
+                        P[ch * 4 + 0] = v.x; P[ch * 4 + 1] = v.y; P[ch * 4 + 2] = v.z; P[ch * 4 + 3] = v.w;
                     }
-                    // phase 1 — independent adds (fma pipe): T[k] = H_diag + s, in place in P
-                    P[0] = __vadd2(hin_prev, P[0]);
-#pragma unroll
-                    for (int k = 1; k < K; ++k) P[k] = __vadd2(Ho[k - 1], P[k]);
-                    hin_prev = h_in;
-                    // phase 2 — the dependent chain down this lane's rows
-                    uint32_t up = h_in, F = f_in;
+                    uint32_t up = h_in, F = f_in, h_prev = 0;
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
-                        E[k] = __viaddmax_s16x2(E[k], ext2, Ho[k]);
                         F = __viaddmax_s16x2(F, ext2, up);
-                        const uint32_t h = LOCAL ? __vimax3_s16x2_relu(P[k], E[k], F)
-                                                 : __vimax3_s16x2(P[k], E[k], F);
-                        up = __vadd2(h, open2);
-                        Ho[k] = up;
-                        if (LOCAL) {
-                            // The best cell of a local alignment is always entered by a
-                            // substitution (E/F only ever lower an earlier H), so tracking
-                            // max(H_diag + s) is exact — and gives the sum a second reader,
-                            // which keeps ptxas from folding the add into a VIADDMNMX on the
-                            // alu pipe.
-                            if (k & 1) best = __vimax3_s16x2(best, P[k - 1], P[k]);
-                            else if (k == K - 1) best = __vmaxs2(best, P[k]);
+                        const uint32_t h = LOCAL ? __vimax3_s16x2_relu(Tn[k], E[k], F)
+                                                 : __vimax3_s16x2(Tn[k], E[k], F);
+                        Tn[k] = __vadd2(up, P[k]);              // diagonal term of (k, j+1)
+                        up = __vadd2(h, open2);                 // Ho[k][j]
+                        E[k] = __viaddmax_s16x2(E[k], ext2, up);   // E[k][j+1]
+                        if (LAST) {
+                            if (i0 + k == La - 1) capA = up;
+                            if (i0 + k == Lb - 1) capB = up;
                         }
+                        if (LOCAL) {
+                            if (k & 1) best = __vimax3_s16x2(best, h_prev, h);
+                            else if (k == K - 1) best = __vmaxs2(best, h);
+                        }
+                        h_prev = h;
                     }
                     h_out = up;
                     f_out = F;
-                    if (!LOCAL) {
-                        if (j == Ls - 1) {          // last column: pick H[L-1][Ls-1] of each half
-#pragma unroll
-                            for (int k = 0; k < K; ++k) {
-                                if (i0 + k == La - 1) capA = Ho[k];
-                                if (i0 + k == Lb - 1) capB = Ho[k];
-                            }
-                        }
+                    if (!LOCAL) top_h = __vadd2(top_h, ext2);
+                };
+                if (!LOCAL && c1 == TOK_BOUNDARY) column(std::true_type{});
+                else column(std::false_type{});
+            } else if (c == TOK_BOUNDARY) {
+                // ================= cold path: the subject just ended ====================
+                const int s = s_first + ord * NGROUPS;
+                if (LOCAL) {
+                    int *slot = my_best + (ord & 31) * 2;
+                    const int lo = (int)(int16_t)(best & 0xFFFFu), hi = (int)(int16_t)(best >> 16);
+                    if (t != G - 1) {
+                        if (lo > 0) atomicMax(slot, lo);
+                        if (hi > 0) atomicMax(slot + 1, hi);
+                    } else {                    // every other lane passed this boundary earlier
+                        const int a = max(lo, atomicExch(slot, 0));
+                        const int b = max(hi, atomicExch(slot + 1, 0));
+                        emit_pair(p, qa, s, a);
+                        emit_pair(p, qb, s, b);
                     }
+                } else {
+                    // captured by the final-column pass of the lanes that own those rows
+                    if (i0 <= La - 1 && La - 1 < i0 + K) emit_pair(p, qa, s, (int)(int16_t)(capA & 0xFFFFu) - p.open);
+                    if (i0 <= Lb - 1 && Lb - 1 < i0 + K) emit_pair(p, qb, s, (int)(int16_t)(capB >> 16) - p.open);
+                }
+                ++ord;
+                if (ord < n_g) {
+                    const uint8_t *sn = p.codes + p.seq_off[s_first + ord * NGROUPS];
+                    c1 = __ldg(sn);
+                    c2 = __ldg(sn + 1);
+                    ptr = sn + 2;
+                    begin_subject(c1);
+                } else {
+                    c1 = TOK_IDLE;
+                    c2 = TOK_IDLE;
+                    ptr = idle_ptr;
+                    inc = 0;
+                }
+            } else if (wait > 0) {
+                // ================= cold path: wind-up of lane t (t idle steps) ===========
+                if (--wait == 0) {
+                    const uint8_t *s0 = p.codes + p.seq_off[s_first];
+                    c1 = __ldg(s0);
+                    c2 = __ldg(s0 + 1);
+                    ptr = s0 + 2;
+                    inc = 1;
+                    begin_subject(c1);
                 }
             }
-
-            int32_t ra, rb;
-            if (LOCAL) {
-#pragma unroll
-                for (int off = G / 2; off > 0; off >>= 1)
-                    best = __vmaxs2(best, __shfl_xor_sync(FULL, best, off, G));
-                ra = (int32_t)(int16_t)(best & 0xFFFFu);
-                rb = (int32_t)(int16_t)(best >> 16);
-            } else {
-                const uint32_t a = __shfl_sync(FULL, capA, (La - 1) / K, G);
-                const uint32_t b = __shfl_sync(FULL, capB, (Lb > 0 ? Lb - 1 : 0) / K, G);
-                ra = (int32_t)(int16_t)(a & 0xFFFFu) - p.open;      // captured Ho = H + open
-                rb = (int32_t)(int16_t)(b >> 16) - p.open;
-            }
-            if (t == 0 && valid) {
-                emit_pair(p, qa, s, ra);
-                emit_pair(p, qb, s, rb);
-            }
+            c = c1;
+            c1 = c2;
         }
     }
 }

@@ -5,11 +5,12 @@
 namespace bgca {
 
 // ---------------------------------------------------------------------------
-// K1: ASCII -> residue codes, written in SORTED order, each sequence padded to
-// a 16-byte multiple with BGCA_PAD_CODE.  One warp per sequence; each lane
+// K1: ASCII -> residue codes, written in SORTED order, each sequence followed by
+// at least one BGCA_PAD_CODE byte (the DP kernels read it as the end-of-subject
+// token) and padded to a 16-byte multiple.  One warp per sequence; each lane
 // encodes 16 residues and issues one 128-bit store, so the write side is
 // fully coalesced; the read side is byte loads that L1 merges into full lines.
-// Algorithmic bytes: sum(L) read + sum(roundup16(L)) written.
+// Algorithmic bytes: sum(L) read + sum(roundup16(L+1)) written.
 // A letter outside the alphabet is reported through err_word =
 // (original sequence index << 32) | position, smallest wins; ~0 = no error.
 // ---------------------------------------------------------------------------
@@ -42,7 +43,7 @@ pack_kernel(const uint8_t *__restrict__ ascii, const int64_t *__restrict__ offse
         const int orig = order[r];
         const uint8_t *src = ascii + offsets_orig[orig];
         const int len = seq_len[r];
-        const int padded = (len + 15) & ~15;
+        const int padded = (len + 1 + 15) & ~15;
         uint4 *dst = reinterpret_cast<uint4 *>(codes + seq_off[r]);
         for (int base = lane * 16; base < padded; base += 32 * 16) {
             uint32_t w[4] = {0, 0, 0, 0};

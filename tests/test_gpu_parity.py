@@ -117,7 +117,7 @@ def test_packer_matches_oracle_encoding():
     assert (lens[order] == np.sort(lens)).all() and sorted(order.tolist()) == list(range(len(seqs)))
     for r, o in enumerate(order):
         seg = codes[offs[r]:offs[r + 1]]
-        assert offs[r] % 16 == 0 and len(seg) == (lens[o] + 15) // 16 * 16
+        assert offs[r] % 16 == 0 and len(seg) == (lens[o] + 16) // 16 * 16
         assert (seg[: lens[o]] == oracle.encode(seqs[o])).all()
         assert (seg[lens[o]:] == 24).all()
 

@@ -14,7 +14,7 @@ from bgclib_b200 import engine as eng
 from bgclib_b200 import extract, plan_host, synth
 from bgclib_b200.alphabet import resolve_matrix
 from fakes import FakeProteinCollection, FakeProtein, build_collection
-from systolic_model import systolic_score
+from systolic_model import systolic_score, systolic_stream
 
 ROOT = Path(__file__).resolve().parent.parent
 
@@ -191,3 +191,25 @@ def test_systolic_model_equals_oracle(local):
             for o, e in ((-12, -1), (-4, -2)):
                 want = oracle.score(q, s, mode=0 if local else 1, open_gap=o, extend_gap=e)
                 assert systolic_score(q.tolist(), s.tolist(), sub, o, e, local, G, K) == want
+
+
+@pytest.mark.parametrize("local", [True, False])
+def test_systolic_stream_of_subjects(local):
+    """Back-to-back subjects through one group: boundary tokens, state reset, wind-up lag,
+    score collection — including subjects shorter than the group is wide."""
+    rng = np.random.default_rng(7)
+    sub = oracle.BLOSUM62.astype(int).tolist()
+    for G, K in ((4, 6), (8, 3), (16, 2)):
+        for _ in range(6):
+            la = int(rng.integers(1, G * K + 1))
+            q = rng.integers(0, 24, la).astype(np.uint8)
+            subjects = []
+            for n in rng.integers(1, 40, size=int(rng.integers(1, 9))):
+                s = rng.integers(0, 24, int(n)).astype(np.uint8)
+                if rng.random() < 0.5:
+                    s = np.concatenate([q, s])[: int(n)].astype(np.uint8)
+                subjects.append(s)
+            subjects += [np.array([3], np.uint8), np.array([5, 5], np.uint8)]     # shorter than G
+            got = systolic_stream(q.tolist(), [s.tolist() for s in subjects], sub, -12, -1, local, G, K)
+            want = [oracle.score(q, s, mode=0 if local else 1) for s in subjects]
+            assert got == want
