@@ -43,11 +43,12 @@ constexpr int kMaxPackedRows = 32 * 32;   // largest G*K
 constexpr int kSubjectsPerGroup = 16;
 constexpr uint64_t kPackedHeader = 64;    // bytes of TOK_IDLE (25) in front of the first sequence
 
-// Relative issue cost of sweeping one subject of length ~Lq with variant (G,K):
-// (steps) x (instructions per step) x (share of the warp one alignment uses).
-double variant_cost(int G, int K, int Lq)
+// Relative issue cost per subject column with variant (G,K): (instructions per step:
+// 5.5 per row + ~21 of step overhead + one LDS.128 per 4 rows) x (share of the warp one
+// alignment uses).  Subjects are streamed, so there is no per-subject wind-up term.
+double variant_cost(int G, int K, int /*Lq*/)
 {
-    return (double)(Lq + G - 1) * (5.5 * K + 14.0) * (double)G;
+    return (5.5 * K + 21.0 + (K + 3) / 4) * (double)G;
 }
 
 // BGCA_FORCE_G=8|16|32 restricts the planner to one group width (tuning aid).
@@ -244,6 +245,11 @@ struct bgca_engine {
     int last_launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
+    // side streams: the per-variant DP kernels are persistent, so launching them on
+    // different streams lets the tail of one overlap the head of the next
+    static constexpr int kSideStreams = 4;
+    cudaStream_t side[kSideStreams] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[kSideStreams] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 extern "C" {
@@ -272,6 +278,11 @@ int bgca_create(int device, bgca_engine **out)
     E->n_sm = prop.multiProcessorCount;
     CUDA_TRY(cudaEventCreate(&E->ev0));
     CUDA_TRY(cudaEventCreate(&E->ev1));
+    CUDA_TRY(cudaEventCreateWithFlags(&E->ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < bgca_engine::kSideStreams; ++i) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&E->side[i], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&E->ev_join[i], cudaEventDisableTiming));
+    }
     *out = E;
     return BGCA_OK;
 }
@@ -286,6 +297,11 @@ int bgca_destroy(bgca_engine *e)
     e->d_seq_off.release(); e->d_err.release(); e->d_tiles.release(); e->d_scratch.release();
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    for (int i = 0; i < bgca_engine::kSideStreams; ++i) {
+        if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
+        if (e->side[i]) cudaStreamDestroy(e->side[i]);
+    }
     delete e;
     return BGCA_OK;
 }
@@ -543,6 +559,8 @@ int bgca_score(bgca_engine *e, int32_t *scores, int32_t *rowbest, int32_t *selfs
     CUDA_TRY(e->d_counters.reserve(runs.size() + 1));
     CUDA_TRY(cudaMemsetAsync(e->d_counters.p, 0, sizeof(int32_t) * (runs.size() + 1), st));
     CUDA_TRY(cudaEventRecord(e->ev0, st));
+    CUDA_TRY(cudaEventRecord(e->ev_fork, st));
+    int n_side_used = 0;
     for (size_t r = 0; r < runs.size(); ++r) {
         const size_t b = runs[r].first, en = runs[r].second;
         const int variant = e->tiles[b].variant;
@@ -585,11 +603,25 @@ int bgca_score(bgca_engine *e, int32_t *scores, int32_t *rowbest, int32_t *selfs
         if (e->open == -12 && e->extend == -1) preset = 1;
         else if (e->open == -11 && e->extend == -1) preset = 2;
         if (std::getenv("BGCA_NO_PRESET")) preset = 0;   // tuning aid: force the run-time-gap kernels
-        if (gi >= 0) err = table[gi][local ? 0 : 1][preset](K, p, e->n_sm, st, &grid);
+        // variants round-robin over the side streams; the caller's stream joins them below
+        cudaStream_t ks = st;
+        if (runs.size() > 1) {
+            const int si = (int)(r % bgca_engine::kSideStreams);
+            ks = e->side[si];
+            if (si >= n_side_used) {
+                CUDA_TRY(cudaStreamWaitEvent(ks, e->ev_fork, 0));
+                n_side_used = si + 1;
+            }
+        }
+        if (gi >= 0) err = table[gi][local ? 0 : 1][preset](K, p, e->n_sm, ks, &grid);
         if (err != cudaSuccess)
             return fail(BGCA_ERR_CUDA, std::string("DP kernel launch (G=") + std::to_string(G) + ",K=" +
                                            std::to_string(K) + "): " + cudaGetErrorString(err));
         e->last_launches++;
+    }
+    for (int i = 0; i < n_side_used; ++i) {
+        CUDA_TRY(cudaEventRecord(e->ev_join[i], e->side[i]));
+        CUDA_TRY(cudaStreamWaitEvent(st, e->ev_join[i], 0));
     }
     CUDA_TRY(cudaEventRecord(e->ev1, st));
     e->timed = true;

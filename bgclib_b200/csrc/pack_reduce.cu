@@ -95,8 +95,9 @@ cudaError_t launch_s32(int mode, const ScoreParams &p, const int32_t *pq, const 
 
 // ---------------------------------------------------------------------------
 // K5 second stage.  best[a][b] = sum over the domains d of BGC a of
-// rowbest[d][b] (int64).  Grid (ceil(B/256), B): thread = one column b, the
-// loop walks the rows of BGC a, so every load is a coalesced 1 KB row segment.
+// rowbest[d][b] (int64).  Grid (ceil(B/1024), B): a thread owns 4 adjacent
+// columns (one 128-bit load per row), rows are walked 4 at a time so 4 loads are
+// in flight per thread; every warp reads 512 contiguous bytes per row.
 // Algorithmic bytes: 4*N*B read + 8*B*B written.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -105,12 +106,35 @@ bgc_sum_kernel(const int32_t *__restrict__ rowbest, const int32_t *__restrict__ 
                int32_t n_bgc, int64_t *__restrict__ best, int64_t *__restrict__ selfsum)
 {
     const int a = blockIdx.y;
-    const int b = blockIdx.x * 256 + threadIdx.x;
+    const int b0 = (blockIdx.x * 256 + threadIdx.x) * 4;
     const int d0 = bgc_start[a], d1 = bgc_start[a + 1];
-    if (b < n_bgc) {
-        long long acc = 0;
-        for (int i = d0; i < d1; ++i) acc += rowbest[(size_t)bgc_doms[i] * n_bgc + b];
-        best[(size_t)a * n_bgc + b] = acc;
+    if (b0 < n_bgc) {
+        long long acc[4] = {0, 0, 0, 0};
+        if ((n_bgc & 3) == 0) {             // rows are 16-byte aligned: vector loads
+            int i = d0;
+            for (; i + 4 <= d1; i += 4) {
+                int4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    v[u] = __ldg(reinterpret_cast<const int4 *>(rowbest + (size_t)bgc_doms[i + u] * n_bgc + b0));
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { acc[0] += v[u].x; acc[1] += v[u].y; acc[2] += v[u].z; acc[3] += v[u].w; }
+            }
+            for (; i < d1; ++i) {
+                const int4 v = __ldg(reinterpret_cast<const int4 *>(rowbest + (size_t)bgc_doms[i] * n_bgc + b0));
+                acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+            }
+        } else {
+            for (int i = d0; i < d1; ++i) {
+                const int32_t *row = rowbest + (size_t)bgc_doms[i] * n_bgc + b0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (b0 + u < n_bgc) acc[u] += row[u];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (b0 + u < n_bgc) best[(size_t)a * n_bgc + b0 + u] = acc[u];
     }
     if (blockIdx.x == 0 && threadIdx.x == 0 && selfsum) {
         long long acc = 0;
@@ -119,32 +143,49 @@ bgc_sum_kernel(const int32_t *__restrict__ rowbest, const int32_t *__restrict__ 
     }
 }
 
+// sim[a][b] = (best[a][b] + best[b][a]) / (selfsum[a] + selfsum[b]).  32x32 tiles; the
+// transposed operand goes through shared memory so both reads are coalesced.
 __global__ void __launch_bounds__(256)
 bgc_sim_kernel(const int64_t *__restrict__ best, const int64_t *__restrict__ selfsum, int32_t n_bgc,
                double *__restrict__ sim)
 {
-    const int a = blockIdx.y;
-    const int b = blockIdx.x * 256 + threadIdx.x;
-    if (b >= n_bgc) return;
-    const long long den = selfsum[a] + selfsum[b];
-    double v = 0.0;
-    if (den > 0) {
-        const long long num = best[(size_t)a * n_bgc + b] + best[(size_t)b * n_bgc + a];
-        v = __ddiv_rn((double)num, (double)den);   // one correctly-rounded IEEE divide
+    __shared__ long long tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+    const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
+    // tile[i][j] = best[b0 + i][a0 + j]
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int bi = b0 + r, aj = a0 + tx;
+        tile[r][tx] = (bi < n_bgc && aj < n_bgc) ? best[(size_t)bi * n_bgc + aj] : 0;
     }
-    if (a == b && selfsum[a] > 0) v = 1.0;
-    sim[(size_t)a * n_bgc + b] = v;
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int a = a0 + r, b = b0 + tx;
+        if (a < n_bgc && b < n_bgc) {
+            const long long sa = selfsum[a], sb = selfsum[b];
+            const long long den = sa + sb;
+            double v = 0.0;
+            if (den > 0) {
+                const long long num = best[(size_t)a * n_bgc + b] + tile[tx][r];
+                v = __ddiv_rn((double)num, (double)den);   // one correctly-rounded IEEE divide
+            }
+            if (a == b && sa > 0) v = 1.0;
+            sim[(size_t)a * n_bgc + b] = v;
+        }
+    }
 }
 
 cudaError_t launch_bgc_reduce(const int32_t *rowbest, const int32_t *selfsc, const int32_t *bgc_start,
                               const int32_t *bgc_doms, int32_t n_bgc, int64_t *best, int64_t *selfsum,
                               double *sim, cudaStream_t st)
 {
-    dim3 grid((n_bgc + 255) / 256, n_bgc);
+    dim3 grid((n_bgc + 1023) / 1024, n_bgc);
     bgc_sum_kernel<<<grid, 256, 0, st>>>(rowbest, selfsc, bgc_start, bgc_doms, n_bgc, best, selfsum);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess || !sim) return err;
-    bgc_sim_kernel<<<grid, 256, 0, st>>>(best, selfsum, n_bgc, sim);
+    dim3 grid2((n_bgc + 31) / 32, (n_bgc + 31) / 32);
+    bgc_sim_kernel<<<grid2, 256, 0, st>>>(best, selfsum, n_bgc, sim);
     return cudaGetLastError();
 }
 

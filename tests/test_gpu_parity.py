@@ -259,3 +259,29 @@ def test_e2e_host_call_matches():
     out = eng.score_all_host(col.ascii, col.offsets)
     assert (out == oracle.all_pairs(col.sequences())).all()
     assert eng.last_launches() >= 1 and eng.last_dp_ms() > 0
+
+
+@pytest.mark.parametrize("n,B", [(40, 5), (64, 8), (300, 36), (1000, 64), (777, 129)])
+def test_k5_reduction_kernels_vs_numpy(n, B):
+    """K5 second stage in isolation (vector and scalar row paths, transposed read)."""
+    import torch
+    rng = np.random.default_rng(n + B)
+    seqs = ["ACDEFGHIKL"[: int(rng.integers(3, 10))] for _ in range(n)]
+    bgc_of = rng.integers(0, B, n).astype(np.int32)
+    bgc_of[: min(n, B - 1)] = np.arange(min(n, B - 1))          # most BGCs non-empty, the last one empty
+    eng = get_engine()
+    eng.set_scoring()
+    eng.pack(seqs, type_of_seq=np.zeros(n, np.int32), bgc_of_seq=bgc_of, n_bgc=B)
+    rowbest = rng.integers(0, 2000, (n, B)).astype(np.int32)
+    selfsc = rng.integers(0, 3000, n).astype(np.int32)
+    sim, best, selfsum = eng.reduce_bgc(torch.from_numpy(rowbest).cuda(), torch.from_numpy(selfsc).cuda())
+    want_best = np.zeros((B, B), np.int64)
+    np.add.at(want_best, bgc_of, rowbest.astype(np.int64))
+    want_self = np.zeros(B, np.int64)
+    np.add.at(want_self, bgc_of, selfsc.astype(np.int64))
+    den = want_self[:, None] + want_self[None, :]
+    num = (want_best + want_best.T).astype(np.float64)
+    want_sim = np.where(den > 0, num / np.where(den > 0, den, 1), 0.0)
+    want_sim[np.arange(B), np.arange(B)] = np.where(want_self > 0, 1.0, 0.0)
+    assert (best.cpu().numpy() == want_best).all() and (selfsum.cpu().numpy() == want_self).all()
+    assert (sim.cpu().numpy() == want_sim).all()
