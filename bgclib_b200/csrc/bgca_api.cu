@@ -58,14 +58,17 @@ int forced_group_width()
     return s ? std::atoi(s) : 0;
 }
 
-int pick_variant(int Lq)
+int pick_variant(int Lq, int mode)
 {
     int best = 0;
     double best_cost = 0.0;
     const int force_g = forced_group_width();
+    // global-mode kernels carry a second (final-column) copy of the column pass and spill
+    // beyond K = 19 at two CTAs per SM: stay below that whenever a wider group covers Lq
+    const int k_cap = (mode == BGCA_MODE_GLOBAL && Lq <= 32 * 19) ? 19 : 32;
     for (int v = 0; v < kNumVariants; ++v) {
         const int G = kVariants[v].G, K = kVariants[v].K;
-        if (G * K < Lq) continue;
+        if (G * K < Lq || K > k_cap) continue;
         if (force_g && G != force_g && force_g * 32 >= Lq) continue;
         const double c = variant_cost(G, K, Lq);
         if (!best || c < best_cost) {
@@ -103,7 +106,12 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, int32_t n, int sam
     std::vector<int64_t> pre(n + 1, 0);
     for (int i = 0; i < n; ++i) pre[i + 1] = pre[i] + len[i];
 
+    // subjects per alignment group and tile: 16 keeps >= 100 tiles per CTA slot on small
+    // batches; large batches take longer tiles so the tile list (and the plan time) stays bounded
+    const int spg = std::min(64, std::max(kSubjectsPerGroup, n / 1250));
+
     std::vector<bgca_tile> all;
+    all.reserve((size_t)n * ((size_t)n / (2 * 128 * (size_t)spg) + 2) / 2);
     int tb = 0;
     while (tb < n) {
         int te = n;
@@ -115,13 +123,13 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, int32_t n, int sam
             const int qb = (qa + 1 < te) ? qa + 1 : -1;
             const int La = len[qa], Lb = (qb >= 0) ? len[qb] : 0;
             const int Lq = std::max(La, Lb);
-            int variant = pick_variant(Lq);
+            int variant = pick_variant(Lq, mode);
             const int G = variant >> 8;
             const int S = te - qa;
             // subjects per tile: ~kSubjectsPerGroup per alignment group (= subject stream) of
             // the CTA, split evenly over the row and rounded up to a whole number per group
             const int ngroups = variant ? CTA_THREADS / G : 16;
-            const int s_max = ngroups * kSubjectsPerGroup;
+            const int s_max = ngroups * spg;
             const int nchunks = (S + s_max - 1) / s_max;
             int chunk = (S + nchunks - 1) / nchunks;
             chunk = (chunk + ngroups - 1) / ngroups * ngroups;

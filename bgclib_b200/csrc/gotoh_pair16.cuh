@@ -75,7 +75,7 @@ struct Pair16Cfg {
     // registers: 2K state + 4CH profile + ~24 -> pick CTAs/SM so ptxas has room.  Global mode
     // carries a second (final-column) copy of the column pass and needs a few more.
     static constexpr int MIN_CTAS_LOCAL = (K <= 8) ? 5 : (K <= 14) ? 4 : (K <= 18) ? 3 : 2;
-    static constexpr int MIN_CTAS_GLOBAL = (K <= 8) ? 4 : (K <= 16) ? 3 : (K <= 18) ? 2 : 1;
+    static constexpr int MIN_CTAS_GLOBAL = (K <= 8) ? 4 : (K <= 16) ? 3 : 2;
 };
 
 // Gap presets: with the gap scores known at compile time the DPX ops take them as
@@ -189,13 +189,19 @@ gotoh_pair16_kernel(const ScoreParams p)
                 const uint4 v = lds128(a + ch * (G * 16));
                 P[ch * 4 + 0] = v.x; P[ch * 4 + 1] = v.y; P[ch * 4 + 2] = v.z; P[ch * 4 + 3] = v.w;
             }
+            // Ho[i0+k][-1], walked down the rows.  The empty asm makes the start value opaque so
+            // the K loop-invariant boundary words are rebuilt here (cold path) instead of being
+            // hoisted into 2K registers that would stay live across the hot loop.
+            uint32_t col = LOCAL ? open2 : pack2(2 * p.open + i0 * p.extend);
+            asm volatile("" : "+r"(col));
+            uint32_t above = hin0;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                const uint32_t above = (k == 0) ? hin0
-                                                : (LOCAL ? open2 : pack2(2 * p.open + (i0 + k - 1) * p.extend));
                 Tn[k] = __vadd2(above, P[k]);
                 // E advanced to column 0 = max(-inf + ext, Ho[i0+k][-1]); local: any value <= 0 is inert
-                E[k] = LOCAL ? 0u : pack2(2 * p.open + (i0 + k) * p.extend);
+                E[k] = LOCAL ? 0u : col;
+                above = col;
+                if (!LOCAL) col = __vadd2(col, ext2);
             }
             best = 0;
             top_h = LOCAL ? open2 : pack2(2 * p.open);
