@@ -51,19 +51,24 @@ def _dist():
 @dataclass
 class DomainPairScores:
     scores: np.ndarray              # int32 [n, n], symmetric, diagonal = self scores
-    index: List[DomainRecord]       # row/column identity
-    computed: Optional[np.ndarray]  # bool [n, n] when same_type_only masked some pairs, else None
+                                    # (query-vs-database: [n_query, n_db])
+    index: List[DomainRecord]       # row identity (and column identity when database is None)
+    computed: Optional[np.ndarray]  # bool, same shape, when same_type_only masked some pairs, else None
     plan: dict                      # tile-plan statistics of this rank
+    db_index: Optional[List[DomainRecord]] = None   # column identity of a query-vs-database run
 
 
 @dataclass
 class BGCSimilarity:
-    sim: np.ndarray                 # float64 [B, B]
-    best: np.ndarray                # int64   [B, B]
-    self_score: np.ndarray          # int64   [B]
-    bgc_ids: List[str]
+    sim: np.ndarray                 # float64 [B, B]           (query-vs-database: [B_query, B_db])
+    best: np.ndarray                # int64   [B, B]            best[a, b] = sum_{d in a} rowbest[d, b]
+    self_score: np.ndarray          # int64   [B]               (rows)
+    bgc_ids: List[str]              # row identity (and column identity when database is None)
     index: List[DomainRecord]
     plan: dict
+    db_bgc_ids: Optional[List[str]] = None          # column identity of a query-vs-database run
+    db_self_score: Optional[np.ndarray] = None      # int64 [B_db]
+    best_db: Optional[np.ndarray] = None            # int64 [B_db, B_query]: the database -> query direction
 
 
 def _as_batch(source, unit, cbp_only, alias, domain_types) -> DomainBatch:
@@ -72,7 +77,22 @@ def _as_batch(source, unit, cbp_only, alias, domain_types) -> DomainBatch:
     return extract(source, unit=unit, cbp_only=cbp_only, alias=alias, domain_types=domain_types)
 
 
-def domain_pair_scores(source, *, mode="local", matrix="BLOSUM62", open_gap_score=-12,
+def _merge(q: DomainBatch, d: DomainBatch):
+    """Query batch followed by database batch: one sequence list, a shared type-id space and
+    the BGC index space [query BGCs | database BGCs] (ids are NOT merged across the two sides)."""
+    type_names = list(q.type_names)
+    pos = {t: i for i, t in enumerate(type_names)}
+    for t in d.type_names:
+        if t not in pos:
+            pos[t] = len(type_names)
+            type_names.append(t)
+    d_types = np.asarray([pos[t] for t in d.type_names], dtype=np.int32)
+    types = np.concatenate([q.type_of_seq, d_types[d.type_of_seq] if len(d) else d.type_of_seq]).astype(np.int32)
+    bgcs = np.concatenate([q.bgc_of_seq, d.bgc_of_seq + len(q.bgc_ids)]).astype(np.int32)
+    return q.sequences + d.sequences, types, bgcs
+
+
+def domain_pair_scores(source, *, database=None, mode="local", matrix="BLOSUM62", open_gap_score=-12,
                        extend_gap_score=-1, unit="domain", cbp_only=True, alias=None,
                        domain_types=None, same_type_only=False, device=None,
                        return_device=False) -> DomainPairScores:
@@ -82,6 +102,10 @@ def domain_pair_scores(source, *, mode="local", matrix="BLOSUM62", open_gap_scor
     outside ``ARNDCQEGHILKMFPSTWYVBZX*`` (as Biopython's PairwiseAligner would).
     Pairs skipped by ``same_type_only`` hold 0 (local) / INT32_MIN (global) and
     are flagged False in ``computed``.
+
+    ``database``: a second collection — only query x database pairs are scored ("a new set of
+    BGCs against a precomputed database", BGClib/Readme.md:18) and ``scores`` is
+    [n_query, n_database].
     """
     batch = _as_batch(source, unit, cbp_only, alias, domain_types)
     n = len(batch)
@@ -91,9 +115,19 @@ def domain_pair_scores(source, *, mode="local", matrix="BLOSUM62", open_gap_scor
     eng.set_scoring(matrix, open_gap_score, extend_gap_score, mode)
     torch = eng.torch
     dist, rank, world = _dist()
-    eng.pack(batch.sequences, type_of_seq=batch.type_of_seq if same_type_only else None)
-    plan = eng.plan(same_type_only=same_type_only, rank=rank, world=world)
-    scores = torch.full((n, n), INT32_MIN, dtype=torch.int32, device=eng.tdev)
+    db = None
+    if database is not None:
+        db = _as_batch(database, unit, cbp_only, alias, domain_types)
+        if len(db) == 0:
+            raise ValueError("no domain sequences selected in the database")
+        seqs, types, _ = _merge(batch, db)
+        eng.pack(seqs, type_of_seq=types if same_type_only else None, n_query=n)
+        plan = eng.plan(same_type_only=same_type_only, rank=rank, world=world, cross_only=True)
+        scores = torch.full((n, len(db)), INT32_MIN, dtype=torch.int32, device=eng.tdev)
+    else:
+        eng.pack(batch.sequences, type_of_seq=batch.type_of_seq if same_type_only else None)
+        plan = eng.plan(same_type_only=same_type_only, rank=rank, world=world)
+        scores = torch.full((n, n), INT32_MIN, dtype=torch.int32, device=eng.tdev)
     eng.score(scores=scores)
     if dist is not None:
         dist.all_reduce(scores, op=dist.ReduceOp.MAX)
@@ -102,13 +136,14 @@ def domain_pair_scores(source, *, mode="local", matrix="BLOSUM62", open_gap_scor
         computed = scores != INT32_MIN
         if resolve_mode(mode) == MODE_LOCAL:
             scores = torch.where(computed, scores, torch.zeros_like(scores))
+    db_index = None if db is None else db.records
     if return_device:
-        return DomainPairScores(scores, batch.records, computed, plan)
+        return DomainPairScores(scores, batch.records, computed, plan, db_index)
     return DomainPairScores(scores.cpu().numpy(), batch.records,
-                            None if computed is None else computed.cpu().numpy(), plan)
+                            None if computed is None else computed.cpu().numpy(), plan, db_index)
 
 
-def bgc_similarity(source, *, matrix="BLOSUM62", open_gap_score=-12, extend_gap_score=-1,
+def bgc_similarity(source, *, database=None, matrix="BLOSUM62", open_gap_score=-12, extend_gap_score=-1,
                    unit="domain", cbp_only=True, alias=None, domain_types=None, same_type_only=True,
                    bgc_ids=None, device=None, return_device=False) -> BGCSimilarity:
     """BGC x BGC similarity from local domain-pair scores:
@@ -121,8 +156,14 @@ def bgc_similarity(source, *, matrix="BLOSUM62", open_gap_score=-12, extend_gap_
     The domain-pair matrix is never materialised: the DP kernels' epilogue does the
     segmented max (atomicMax into rowbest), a second kernel the segmented sums.
     ``bgc_ids`` fixes the row order (ids absent from ``source`` get zero rows).
+    ``database``: a second collection — rows are the BGCs of ``source``, columns the BGCs of
+    ``database``; only query x database domain pairs (and self pairs) are aligned.
     """
     batch = _as_batch(source, unit, cbp_only, alias, domain_types)
+    if database is not None:
+        return _bgc_similarity_cross(batch, _as_batch(database, unit, cbp_only, alias, domain_types),
+                                     matrix, open_gap_score, extend_gap_score, same_type_only, device,
+                                     return_device)
     ids = list(batch.bgc_ids)
     bgc_of = batch.bgc_of_seq
     if bgc_ids is not None:
@@ -157,6 +198,36 @@ def bgc_similarity(source, *, matrix="BLOSUM62", open_gap_score=-12, extend_gap_
         return BGCSimilarity(sim, best, selfsum, ids, batch.records, plan)
     return BGCSimilarity(sim.cpu().numpy(), best.cpu().numpy(), selfsum.cpu().numpy(), ids,
                          batch.records, plan)
+
+
+def _bgc_similarity_cross(q: DomainBatch, d: DomainBatch, matrix, open_gap_score, extend_gap_score,
+                          same_type_only, device, return_device) -> BGCSimilarity:
+    Bq, Bd = len(q.bgc_ids), len(d.bgc_ids)
+    if Bq == 0 or Bd == 0 or len(q) == 0 or len(d) == 0:
+        raise ValueError("query and database must both hold BGCs with domain sequences")
+    seqs, types, bgcs = _merge(q, d)
+    n, B = len(seqs), Bq + Bd
+    eng = get_engine(device)
+    torch = eng.torch
+    eng.set_scoring(matrix, open_gap_score, extend_gap_score, "local")
+    dist, rank, world = _dist()
+    # the packer sorts by (type, role, length): without types the single block is [queries | database]
+    eng.pack(seqs, type_of_seq=types if same_type_only else None, bgc_of_seq=bgcs, n_bgc=B, n_query=len(q))
+    plan = eng.plan(same_type_only=same_type_only, rank=rank, world=world, cross_only=True)
+    rowbest = torch.zeros((n, B), dtype=torch.int32, device=eng.tdev)
+    selfsc = torch.zeros((n,), dtype=torch.int32, device=eng.tdev)
+    eng.score(rowbest=rowbest, selfsc=selfsc, type_check=False)
+    if dist is not None:
+        dist.all_reduce(rowbest, op=dist.ReduceOp.MAX)
+        dist.all_reduce(selfsc, op=dist.ReduceOp.MAX)
+    sim, best, selfsum = eng.reduce_bgc(rowbest, selfsc)
+    sim_x = sim[:Bq, Bq:].contiguous()
+    best_qd = best[:Bq, Bq:].contiguous()
+    best_dq = best[Bq:, :Bq].contiguous()
+    if not return_device:
+        sim_x, best_qd, best_dq, selfsum = (x.cpu().numpy() for x in (sim_x, best_qd, best_dq, selfsum))
+    return BGCSimilarity(sim_x, best_qd, selfsum[:Bq], list(q.bgc_ids), q.records + d.records, plan,
+                         list(d.bgc_ids), selfsum[Bq:], best_dq)
 
 
 def attach(collection_cls=None):

@@ -93,14 +93,29 @@ bool fits_int16(int mode, int max_abs_sub, int open, int extend, int Lq, int Ls_
     return true;
 }
 
+// cross plans take the queries of a block as its leading run of role-0 sequences: true when
+// every block the planner will cut ([0,n) or one per type) is sorted queries-first.
+bool roles_partitioned(const int32_t *type, const int32_t *role, int32_t n, int same_type_only)
+{
+    for (int i = 1; i < n; ++i) {
+        const bool same_block = !(same_type_only && type) || type[i] == type[i - 1];
+        if (same_block && role[i] < role[i - 1]) return false;
+    }
+    return true;
+}
+
 struct PlanResult {
     std::vector<bgca_tile> tiles;   // this rank's tiles, grouped by variant, heavy first
     bgca_plan_info info{};
 };
 
 // K6 — tile scheduler.  See bgca.h.  All indices are SORTED-space.
-PlanResult make_plan(const int32_t *len, const int32_t *type, int32_t n, int same_type_only, int mode,
-                     int max_abs_sub, int open, int extend, int rank, int world)
+// role (nullable): 0 = query, 1 = database; sorted as (type, role, length).  cross_only: only
+// query x database pairs are planned, plus one self-only tile per sequence pair (reserved = 1)
+// so that the self scores the similarity is normalised with exist.
+PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *role, int32_t n,
+                     int same_type_only, int cross_only, int mode, int max_abs_sub, int open, int extend,
+                     int rank, int world)
 {
     PlanResult R;
     std::vector<int64_t> pre(n + 1, 0);
@@ -119,21 +134,29 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, int32_t n, int sam
             te = tb + 1;
             while (te < n && type[te] == type[tb]) ++te;
         }
-        for (int qa = tb; qa < te; qa += 2) {
-            const int qb = (qa + 1 < te) ? qa + 1 : -1;
+        // queries [tb, tm) and subjects' range; square mode: tm = te and subjects start at qa
+        int tm = te;
+        if (cross_only) {
+            tm = tb;
+            while (tm < te && role[tm] == 0) ++tm;
+        }
+        for (int qa = tb; qa < tm; qa += 2) {
+            const int qb = (qa + 1 < tm) ? qa + 1 : -1;
             const int La = len[qa], Lb = (qb >= 0) ? len[qb] : 0;
             const int Lq = std::max(La, Lb);
             int variant = pick_variant(Lq, mode);
             const int G = variant >> 8;
-            const int S = te - qa;
-            // subjects per tile: ~kSubjectsPerGroup per alignment group (= subject stream) of
-            // the CTA, split evenly over the row and rounded up to a whole number per group
+            const int sub0 = cross_only ? tm : qa;
+            const int S = te - sub0;
+            if (S <= 0) continue;
+            // subjects per tile: ~spg per alignment group (= subject stream) of the CTA,
+            // split evenly over the row and rounded up to a whole number per group
             const int ngroups = variant ? CTA_THREADS / G : 16;
             const int s_max = ngroups * spg;
             const int nchunks = (S + s_max - 1) / s_max;
             int chunk = (S + nchunks - 1) / nchunks;
             chunk = (chunk + ngroups - 1) / ngroups * ngroups;
-            for (int s0 = qa; s0 < te; s0 += chunk) {
+            for (int s0 = sub0; s0 < te; s0 += chunk) {
                 const int s1 = std::min(te, s0 + chunk);
                 bgca_tile T{};
                 T.qa = qa; T.qb = qb; T.s_begin = s0; T.s_end = s1;
@@ -143,11 +166,35 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, int32_t n, int sam
                 all.push_back(T);
             }
         }
+        if (cross_only) {
+            // self-only tiles for every sequence of the block (queries and database alike)
+            for (int r0 = tb; r0 < te;) {
+                const int r_end = (r0 < tm) ? tm : te;          // pairs never straddle the role boundary
+                for (int qa = r0; qa < r_end; qa += 2) {
+                    const int qb = (qa + 1 < r_end) ? qa + 1 : -1;
+                    const int La = len[qa], Lb = (qb >= 0) ? len[qb] : 0;
+                    const int Lq = std::max(La, Lb);
+                    bgca_tile T{};
+                    T.qa = qa; T.qb = qb; T.s_begin = qa; T.s_end = (qb >= 0 ? qb : qa) + 1;
+                    T.variant = pick_variant(Lq, mode);
+                    T.reserved = 1;
+                    if (T.variant && !fits_int16(mode, max_abs_sub, open, extend, Lq, Lq)) T.variant = 0;
+                    T.cells = (int64_t)(La + Lb) * (pre[T.s_end] - pre[T.s_begin]);
+                    all.push_back(T);
+                }
+                r0 = r_end;
+            }
+        }
         tb = te;
     }
 
     // exact accounting of unique pairs (i<=j) per tile
     auto tile_pairs = [&](const bgca_tile &T, int64_t &pairs, int64_t &cells) {
+        if (T.reserved) {                    // self-only tile of a cross plan
+            pairs = (T.qb >= 0) ? 2 : 1;
+            cells = (int64_t)len[T.qa] * len[T.qa] + (T.qb >= 0 ? (int64_t)len[T.qb] * len[T.qb] : 0);
+            return;
+        }
         const int64_t sumL = pre[T.s_end] - pre[T.s_begin];
         pairs = T.s_end - T.s_begin;
         cells = (int64_t)len[T.qa] * sumL;
@@ -232,7 +279,9 @@ struct bgca_engine {
     bool scoring_set = false;
     // packed batch (host mirrors, SORTED space unless named *_orig)
     int32_t n = 0, n_bgc = 0;
-    std::vector<int32_t> len, type, bgc, order, inv_order;
+    std::vector<int32_t> len, type, bgc, role, order, inv_order;
+    int32_t n_query = 0;          // sequences with role 0 (they come first in ORIGINAL order)
+    bool has_role = false, cross_planned = false;
     std::vector<uint32_t> seq_off;
     std::vector<int32_t> bgc_start, bgc_doms;   // CSR over ORIGINAL indices
     int64_t packed_bytes = 0;
@@ -338,12 +387,13 @@ int bgca_set_scoring(bgca_engine *e, const int8_t *sub, int32_t open, int32_t ex
 
 int bgca_pack(bgca_engine *e, const uint8_t *ascii, const int64_t *offsets, int32_t n,
               const int32_t *type_of_seq, const int32_t *bgc_of_seq, int32_t n_bgc,
-              int32_t ascii_on_device, void *stream)
+              int32_t n_query, int32_t ascii_on_device, void *stream)
 {
     if (!e || !ascii || !offsets) return fail(BGCA_ERR_INVALID, "bgca_pack: NULL argument");
     if (n <= 0) return fail(BGCA_ERR_INVALID, "bgca_pack: need at least one sequence");
     if (bgc_of_seq && (n_bgc <= 0 || n_bgc > 65535))
         return fail(BGCA_ERR_RANGE, "bgca_pack: n_bgc must be in 1..65535");
+    if (n_query < 0 || n_query > n) return fail(BGCA_ERR_INVALID, "bgca_pack: n_query must be in 0..n");
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(e->device));
     e->packed = false;
@@ -368,13 +418,20 @@ int bgca_pack(bgca_engine *e, const uint8_t *ascii, const int64_t *offsets, int3
     std::stable_sort(e->order.begin(), e->order.end(), [&](int a, int b) {
         const int ta = type_of_seq ? type_of_seq[a] : 0, tb = type_of_seq ? type_of_seq[b] : 0;
         if (ta != tb) return ta < tb;
+        if (n_query > 0) {                       // queries (original index < n_query) before database
+            const int ra = a >= n_query, rb = b >= n_query;
+            if (ra != rb) return ra < rb;
+        }
         return len_orig[a] < len_orig[b];
     });
     e->n = n;
     e->n_bgc = bgc_of_seq ? n_bgc : 0;
     e->has_type = type_of_seq != nullptr;
     e->has_bgc = bgc_of_seq != nullptr;
-    e->len.resize(n); e->type.assign(n, 0); e->bgc.assign(n, 0); e->seq_off.resize(n);
+    e->n_query = n_query;
+    e->has_role = n_query > 0;
+    e->cross_planned = false;
+    e->len.resize(n); e->type.assign(n, 0); e->bgc.assign(n, 0); e->role.assign(n, 0); e->seq_off.resize(n);
     e->inv_order.resize(n);
     uint64_t off = kPackedHeader;   // header of idle tokens (see gotoh_pair16.cuh)
     for (int r = 0; r < n; ++r) {
@@ -383,6 +440,7 @@ int bgca_pack(bgca_engine *e, const uint8_t *ascii, const int64_t *offsets, int3
         e->len[r] = len_orig[o];
         if (type_of_seq) e->type[r] = type_of_seq[o];
         if (bgc_of_seq) e->bgc[r] = bgc_of_seq[o];
+        e->role[r] = (n_query > 0 && o >= n_query) ? 1 : 0;
         e->seq_off[r] = (uint32_t)off;
         off += (uint64_t)((len_orig[o] + 1 + 15) & ~15);   // >= 1 pad byte = end-of-subject token
         if (off > 0xFFFFFFF0ull) return fail(BGCA_ERR_RANGE, "bgca_pack: packed batch exceeds 4 GiB");
@@ -465,15 +523,18 @@ int bgca_get_packed(const bgca_engine *e, uint8_t *codes_out, int64_t *offsets_s
     return BGCA_OK;
 }
 
-int bgca_plan_host(const int32_t *len_sorted, const int32_t *type_sorted, int32_t n,
-                   int32_t same_type_only, int32_t mode, int32_t max_abs_sub, int32_t open,
-                   int32_t extend, int32_t rank, int32_t world, bgca_tile *tiles_out,
-                   int64_t capacity, int64_t *n_tiles_out, bgca_plan_info *info)
+int bgca_plan_host(const int32_t *len_sorted, const int32_t *type_sorted, const int32_t *role_sorted,
+                   int32_t n, int32_t same_type_only, int32_t cross_only, int32_t mode,
+                   int32_t max_abs_sub, int32_t open, int32_t extend, int32_t rank, int32_t world,
+                   bgca_tile *tiles_out, int64_t capacity, int64_t *n_tiles_out, bgca_plan_info *info)
 {
     if (!len_sorted || n <= 0 || world <= 0 || rank < 0 || rank >= world)
         return fail(BGCA_ERR_INVALID, "bgca_plan_host: bad arguments");
-    PlanResult R = make_plan(len_sorted, type_sorted, n, same_type_only, mode, max_abs_sub, open, extend,
-                             rank, world);
+    if (cross_only && !role_sorted) return fail(BGCA_ERR_INVALID, "bgca_plan_host: cross_only needs roles");
+    if (cross_only && !roles_partitioned(type_sorted, role_sorted, n, same_type_only))
+        return fail(BGCA_ERR_INVALID, "bgca_plan_host: cross_only needs every planned block sorted queries-first");
+    PlanResult R = make_plan(len_sorted, type_sorted, role_sorted, n, same_type_only, cross_only, mode,
+                             max_abs_sub, open, extend, rank, world);
     if (n_tiles_out) *n_tiles_out = (int64_t)R.tiles.size();
     if (info) *info = R.info;
     if (tiles_out) {
@@ -483,16 +544,24 @@ int bgca_plan_host(const int32_t *len_sorted, const int32_t *type_sorted, int32_
     return BGCA_OK;
 }
 
-int bgca_plan(bgca_engine *e, int32_t same_type_only, int32_t rank, int32_t world, bgca_plan_info *info)
+int bgca_plan(bgca_engine *e, int32_t same_type_only, int32_t cross_only, int32_t rank, int32_t world,
+              bgca_plan_info *info)
 {
     if (!e || !e->packed) return fail(BGCA_ERR_INVALID, "bgca_plan: call bgca_pack first");
     if (!e->scoring_set) return fail(BGCA_ERR_INVALID, "bgca_plan: call bgca_set_scoring first");
     if (world <= 0 || rank < 0 || rank >= world) return fail(BGCA_ERR_INVALID, "bgca_plan: bad rank/world");
     if (same_type_only && !e->has_type)
         return fail(BGCA_ERR_INVALID, "bgca_plan: same_type_only needs type_of_seq at pack time");
+    if (cross_only && (!e->has_role || e->n_query >= e->n))
+        return fail(BGCA_ERR_INVALID, "bgca_plan: cross_only needs 0 < n_query < n at pack time");
+    if (cross_only && !roles_partitioned(e->has_type ? e->type.data() : nullptr, e->role.data(), e->n, same_type_only))
+        return fail(BGCA_ERR_INVALID, "bgca_plan: cross_only without same_type_only needs a batch packed "
+                                      "without type_of_seq (the packer sorts by type before role)");
     CUDA_TRY(cudaSetDevice(e->device));
-    PlanResult R = make_plan(e->len.data(), e->has_type ? e->type.data() : nullptr, e->n, same_type_only,
-                             e->mode, e->max_abs_sub, e->open, e->extend, rank, world);
+    PlanResult R = make_plan(e->len.data(), e->has_type ? e->type.data() : nullptr, e->role.data(), e->n,
+                             same_type_only, cross_only, e->mode, e->max_abs_sub, e->open, e->extend, rank,
+                             world);
+    e->cross_planned = cross_only != 0;
     e->tiles.swap(R.tiles);
     e->plan_info = R.info;
     CUDA_TRY(e->d_tiles.reserve(e->tiles.size()));
@@ -524,6 +593,7 @@ static void fill_params(const bgca_engine *e, ScoreParams &p, int32_t *scores, i
     p.open2 = ((uint32_t)e->open & 0xFFFFu) * 0x10001u;
     p.ext2 = ((uint32_t)e->extend & 0xFFFFu) * 0x10001u;
     p.type_check = type_check;
+    p.cross_nq = e->cross_planned ? e->n_query : 0;
     std::memcpy(p.sub, e->sub, NSYM * NSYM);
 }
 
@@ -681,9 +751,9 @@ int bgca_score_all_host(bgca_engine *e, const uint8_t *ascii, const int64_t *off
                         int32_t *scores_host)
 {
     if (!e || !scores_host) return fail(BGCA_ERR_INVALID, "bgca_score_all_host: NULL argument");
-    int rc = bgca_pack(e, ascii, offsets, n, nullptr, nullptr, 0, 0, nullptr);
+    int rc = bgca_pack(e, ascii, offsets, n, nullptr, nullptr, 0, 0, 0, nullptr);
     if (rc != BGCA_OK) return rc;
-    rc = bgca_plan(e, 0, 0, 1, nullptr);
+    rc = bgca_plan(e, 0, 0, 0, 1, nullptr);
     if (rc != BGCA_OK) return rc;
     int32_t *d_scores = nullptr;
     const size_t bytes = sizeof(int32_t) * (size_t)n * (size_t)n;

@@ -33,6 +33,7 @@ struct ScoreParams {
     int32_t open, extend;      // negative scores
     uint32_t open2, ext2;      // the same, replicated in both 16-bit halves
     int32_t type_check;
+    int32_t cross_nq;          // > 0: query-vs-database plan; ORIGINAL indices < cross_nq are queries
     int8_t sub[NSYM * NSYM];
 };
 
@@ -43,7 +44,15 @@ __device__ __forceinline__ void emit_pair(const ScoreParams &p, int q, int s, in
 {
     if (q < 0 || s < q) return;
     const int oq = p.order[q], os = p.order[s];
-    if (p.scores) {
+    if (p.cross_nq > 0) {
+        // query-vs-database: only cross pairs and self pairs count; scores is [n_query x n_db]
+        const bool q_is_query = oq < p.cross_nq, s_is_query = os < p.cross_nq;
+        if (q != s && q_is_query == s_is_query) return;
+        if (p.scores && q != s) {
+            const int row = q_is_query ? oq : os, col = (q_is_query ? os : oq) - p.cross_nq;
+            p.scores[(size_t)row * (p.n - p.cross_nq) + col] = score;
+        }
+    } else if (p.scores) {
         p.scores[(size_t)oq * p.n + os] = score;
         p.scores[(size_t)os * p.n + oq] = score;
     }

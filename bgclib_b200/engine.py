@@ -71,13 +71,13 @@ def load_library():
     lib.bgca_create.argtypes = [ctypes.c_int, P(vp)]
     lib.bgca_destroy.argtypes = [vp]
     lib.bgca_set_scoring.argtypes = [vp, vp, i32, i32, i32]
-    lib.bgca_pack.argtypes = [vp, vp, vp, i32, vp, vp, i32, i32, vp]
+    lib.bgca_pack.argtypes = [vp, vp, vp, i32, vp, vp, i32, i32, i32, vp]
     lib.bgca_packed_bytes.argtypes = [vp]
     lib.bgca_packed_bytes.restype = i64
     lib.bgca_get_packed.argtypes = [vp, vp, vp, vp, vp]
-    lib.bgca_plan.argtypes = [vp, i32, i32, i32, P(PlanInfo)]
-    lib.bgca_plan_host.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, i64, P(i64),
-                                   P(PlanInfo)]
+    lib.bgca_plan.argtypes = [vp, i32, i32, i32, i32, P(PlanInfo)]
+    lib.bgca_plan_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, i64,
+                                   P(i64), P(PlanInfo)]
     lib.bgca_score.argtypes = [vp, vp, vp, vp, i32, vp]
     lib.bgca_score_pairs32.argtypes = [vp, vp, vp, i64, vp, vp]
     lib.bgca_reduce_bgc.argtypes = [vp, vp, vp, vp, vp, vp, vp]
@@ -131,21 +131,21 @@ def concat_ascii(seqs: Sequence[str]):
     return ascii_, offsets
 
 
-def plan_host(len_sorted, type_sorted=None, *, same_type_only=False, mode=MODE_LOCAL,
-              max_abs_sub=11, open_gap=-12, extend_gap=-1, rank=0, world=1):
-    """Host-only K6 planner (no CUDA).  Returns (tiles structured array, info dict)."""
+def plan_host(len_sorted, type_sorted=None, role_sorted=None, *, same_type_only=False, cross_only=False,
+              mode=MODE_LOCAL, max_abs_sub=11, open_gap=-12, extend_gap=-1, rank=0, world=1):
+    """Host-only K6 planner (no CUDA).  Returns (tiles structured array, info dict).
+    Inputs are in SORTED order: by type, then role (0 query / 1 database), then length."""
     lib = load_library()
     lens = np.ascontiguousarray(len_sorted, dtype=np.int32)
     types = None if type_sorted is None else np.ascontiguousarray(type_sorted, dtype=np.int32)
+    roles = None if role_sorted is None else np.ascontiguousarray(role_sorted, dtype=np.int32)
     n_tiles = ctypes.c_int64(0)
     info = PlanInfo()
-    _check(lib.bgca_plan_host(_np_ptr(lens), _np_ptr(types), len(lens), int(same_type_only), mode,
-                              max_abs_sub, open_gap, extend_gap, rank, world, None, 0,
-                              ctypes.byref(n_tiles), ctypes.byref(info)))
+    args = (_np_ptr(lens), _np_ptr(types), _np_ptr(roles), len(lens), int(same_type_only), int(cross_only),
+            mode, max_abs_sub, open_gap, extend_gap, rank, world)
+    _check(lib.bgca_plan_host(*args, None, 0, ctypes.byref(n_tiles), ctypes.byref(info)))
     tiles = (Tile * max(1, n_tiles.value))()
-    _check(lib.bgca_plan_host(_np_ptr(lens), _np_ptr(types), len(lens), int(same_type_only), mode,
-                              max_abs_sub, open_gap, extend_gap, rank, world,
-                              ctypes.cast(tiles, ctypes.c_void_p), n_tiles.value,
+    _check(lib.bgca_plan_host(*args, ctypes.cast(tiles, ctypes.c_void_p), n_tiles.value,
                               ctypes.byref(n_tiles), ctypes.byref(info)))
     arr = np.ctypeslib.as_array(tiles)[: n_tiles.value].copy() if n_tiles.value else \
         np.zeros(0, dtype=np.ctypeslib.as_array(tiles).dtype)
@@ -174,6 +174,8 @@ class Engine:
         self.tdev = torch.device("cuda", self.device)
         self.n = 0
         self.n_bgc = 0
+        self.n_query = 0
+        self.cross = False
         self.mode = MODE_LOCAL
         self.plan_info = None
         self.set_scoring()
@@ -204,12 +206,13 @@ class Engine:
                                           int(extend_gap_score), self.mode))
 
     # ---- K1 ------------------------------------------------------------------
-    def pack(self, seqs: Sequence[str], type_of_seq=None, bgc_of_seq=None, n_bgc: int = 0):
+    def pack(self, seqs: Sequence[str], type_of_seq=None, bgc_of_seq=None, n_bgc: int = 0, n_query: int = 0):
         ascii_, offsets = concat_ascii(seqs)
-        return self.pack_ascii(ascii_, offsets, type_of_seq, bgc_of_seq, n_bgc)
+        return self.pack_ascii(ascii_, offsets, type_of_seq, bgc_of_seq, n_bgc, n_query)
 
-    def pack_ascii(self, ascii_, offsets, type_of_seq=None, bgc_of_seq=None, n_bgc: int = 0):
-        """ascii_: uint8 numpy array (host) or torch uint8 CUDA tensor; offsets int64[n+1] host."""
+    def pack_ascii(self, ascii_, offsets, type_of_seq=None, bgc_of_seq=None, n_bgc: int = 0, n_query: int = 0):
+        """ascii_: uint8 numpy array (host) or torch uint8 CUDA tensor; offsets int64[n+1] host.
+        n_query > 0: the first n_query sequences are queries, the rest a database."""
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         n = len(offsets) - 1
         types = None if type_of_seq is None else np.ascontiguousarray(type_of_seq, dtype=np.int32)
@@ -228,8 +231,10 @@ class Engine:
             ptr = _np_ptr(ascii_) if ascii_.size else ctypes.c_void_p(1)
         with self.torch.cuda.device(self.tdev):
             _check(self._lib.bgca_pack(self._h, ptr, _np_ptr(offsets), n, _np_ptr(types), _np_ptr(bgcs),
-                                       int(n_bgc), int(on_device), self._stream()))
+                                       int(n_bgc), int(n_query), int(on_device), self._stream()))
         self.n = n
+        self.n_query = int(n_query)
+        self.cross = False
         self.n_bgc = int(n_bgc) if bgcs is not None else 0
         self.plan_info = None
 
@@ -243,9 +248,11 @@ class Engine:
         return codes, offs, order
 
     # ---- K6 ------------------------------------------------------------------
-    def plan(self, same_type_only: bool = False, rank: int = 0, world: int = 1) -> dict:
+    def plan(self, same_type_only: bool = False, rank: int = 0, world: int = 1, cross_only: bool = False) -> dict:
         info = PlanInfo()
-        _check(self._lib.bgca_plan(self._h, int(same_type_only), int(rank), int(world), ctypes.byref(info)))
+        _check(self._lib.bgca_plan(self._h, int(same_type_only), int(cross_only), int(rank), int(world),
+                                   ctypes.byref(info)))
+        self.cross = bool(cross_only)
         self.plan_info = info.as_dict()
         return self.plan_info
 
@@ -253,7 +260,8 @@ class Engine:
     def score(self, scores=None, rowbest=None, selfsc=None, type_check: bool = False):
         """Launch the DP kernels over this rank's tiles into caller-owned CUDA
         int32 tensors (asynchronous on the current stream)."""
-        for t, shape in ((scores, (self.n, self.n)), (rowbest, (self.n, self.n_bgc)), (selfsc, (self.n,))):
+        sshape = (self.n_query, self.n - self.n_query) if self.cross else (self.n, self.n)
+        for t, shape in ((scores, sshape), (rowbest, (self.n, self.n_bgc)), (selfsc, (self.n,))):
             if t is not None:
                 if t.dtype != self.torch.int32 or not t.is_cuda or not t.is_contiguous() or tuple(t.shape) != shape:
                     raise ValueError(f"output tensor must be contiguous CUDA int32 of shape {shape}")
@@ -293,6 +301,8 @@ class Engine:
             _check(self._lib.bgca_score_all_host(self._h, _np_ptr(ascii_), _np_ptr(offsets), n, _np_ptr(out)))
         self.n = n
         self.n_bgc = 0
+        self.n_query = 0
+        self.cross = False
         return out
 
     def last_launches(self) -> int:

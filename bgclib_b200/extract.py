@@ -49,6 +49,32 @@ class DomainBatch:
     def __len__(self):
         return len(self.sequences)
 
+    # ---- on-disk form (resumable / repeated runs: a database is extracted once) -------------
+    def save(self, path) -> None:
+        """One .npz: ASCII residues + offsets + type/BGC ids + the identity tables."""
+        offsets = np.zeros(len(self.sequences) + 1, dtype=np.int64)
+        np.cumsum([len(s) for s in self.sequences], out=offsets[1:])
+        np.savez_compressed(
+            path, ascii=np.frombuffer("".join(self.sequences).encode("ascii"), dtype=np.uint8),
+            offsets=offsets, type_of_seq=self.type_of_seq, bgc_of_seq=self.bgc_of_seq,
+            type_names=np.asarray(self.type_names, dtype=object), bgc_ids=np.asarray(self.bgc_ids, dtype=object),
+            protein=np.asarray([r.protein_identifier for r in self.records], dtype=object),
+            domain=np.asarray([r.domain_id for r in self.records], dtype=object),
+            ali=np.asarray([[r.ali_from, r.ali_to] for r in self.records], dtype=np.int64).reshape(-1, 2))
+
+    @classmethod
+    def load(cls, path) -> "DomainBatch":
+        z = np.load(path, allow_pickle=True)
+        blob = z["ascii"].tobytes().decode("ascii")
+        off = z["offsets"]
+        seqs = [blob[off[i]:off[i + 1]] for i in range(len(off) - 1)]
+        type_names, bgc_ids = list(z["type_names"]), list(z["bgc_ids"])
+        recs = [DomainRecord(i, bgc_ids[z["bgc_of_seq"][i]], str(z["protein"][i]), str(z["domain"][i]),
+                             type_names[z["type_of_seq"][i]], int(z["ali"][i][0]), int(z["ali"][i][1]), len(seqs[i]))
+                for i in range(len(seqs))]
+        return cls(seqs, recs, bgc_ids, z["bgc_of_seq"].astype(np.int32), type_names,
+                   z["type_of_seq"].astype(np.int32))
+
 
 def type_key(domain, alias: Optional[dict]) -> str:
     if alias:

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define BGCA_VERSION 100
+#define BGCA_VERSION 101
 
 #define BGCA_MODE_LOCAL 0  /* Smith-Waterman/Gotoh, result = best cell, >= 0        */
 #define BGCA_MODE_GLOBAL 1 /* Needleman-Wunsch/Gotoh, end gaps cost like internal   */
@@ -90,12 +90,15 @@ int bgca_set_scoring(bgca_engine *e, const int8_t *sub, int32_t open, int32_t ex
  * offsets[n+1].  type_of_seq / bgc_of_seq (nullable, length n) carry the domain
  * type key (alias-or-ID rule, BGCtoolkit.py:1511-1513) and the index of the
  * owning BGC (BGCProtein.parent_cluster_id, BGClib/BGClib.py:1835).
+ * n_query > 0 declares the first n_query sequences "queries" and the rest a "database"
+ * (the query-vs-database use BGClib/Readme.md:18 describes: "a new set of BGCs against a
+ * precomputed database"); 0 = one undivided collection.
  * ascii_on_device != 0: `ascii` is a device pointer (offsets/types stay host).
  * The engine sorts by (type, length), encodes to 0..23, pads every sequence to
  * a 16-byte multiple with BGCA_PAD_CODE and keeps the packed batch in HBM. */
 int bgca_pack(bgca_engine *e, const uint8_t *ascii, const int64_t *offsets, int32_t n,
               const int32_t *type_of_seq, const int32_t *bgc_of_seq, int32_t n_bgc,
-              int32_t ascii_on_device, void *stream);
+              int32_t n_query, int32_t ascii_on_device, void *stream);
 
 /* Introspection of the packed batch (host outputs; any pointer may be NULL).
  * codes_out must hold bgca_packed_bytes() bytes. */
@@ -106,16 +109,18 @@ int bgca_get_packed(const bgca_engine *e, uint8_t *codes_out, int64_t *offsets_s
 /* K6 tile scheduler.  Enumerates the upper-triangular pair matrix (i<=j, self
  * pairs included) as tiles, optionally only within a domain type, and assigns
  * tiles to `world` ranks by longest-processing-time on the exact cell count.
+ * cross_only != 0 (needs n_query at pack time): only query x database pairs are planned,
+ * plus the self pair of every sequence (the similarity is normalised with self scores).
  * bgca_plan keeps this rank's tiles on the device for bgca_score(). */
-int bgca_plan(bgca_engine *e, int32_t same_type_only, int32_t rank, int32_t world,
+int bgca_plan(bgca_engine *e, int32_t same_type_only, int32_t cross_only, int32_t rank, int32_t world,
               bgca_plan_info *info);
 
 /* Host-only planner (no CUDA calls): same algorithm on caller-supplied SORTED
  * lengths/types; writes up to `capacity` tiles of `rank` and the tile count.
  * Used by the CPU tests of the scheduler. */
-int bgca_plan_host(const int32_t *len_sorted, const int32_t *type_sorted, int32_t n,
-                   int32_t same_type_only, int32_t mode, int32_t max_abs_sub,
-                   int32_t open, int32_t extend,
+int bgca_plan_host(const int32_t *len_sorted, const int32_t *type_sorted, const int32_t *role_sorted,
+                   int32_t n, int32_t same_type_only, int32_t cross_only, int32_t mode,
+                   int32_t max_abs_sub, int32_t open, int32_t extend,
                    int32_t rank, int32_t world,
                    bgca_tile *tiles_out, int64_t capacity, int64_t *n_tiles_out,
                    bgca_plan_info *info);
@@ -124,6 +129,8 @@ int bgca_plan_host(const int32_t *len_sorted, const int32_t *type_sorted, int32_
  * all optional (NULL to skip), all in ORIGINAL index space, caller-owned and
  * caller-initialised (zero; global mode: any value < every score):
  *   scores   int32[n*n]      s(i,j) and s(j,i) for every owned pair i<=j
+ *            (after a cross_only plan: int32[n_query * (n - n_query)], row = query,
+ *            column = database sequence)
  *   rowbest  int32[n*n_bgc]  atomicMax_{e in bgc b, type(e)==type(d)} s(d,e)
  *   selfsc   int32[n]        s(d,d)
  * type_check != 0 applies the same-type condition inside the epilogue (needed

@@ -285,3 +285,67 @@ def test_k5_reduction_kernels_vs_numpy(n, B):
     want_sim[np.arange(B), np.arange(B)] = np.where(want_self > 0, 1.0, 0.0)
     assert (best.cpu().numpy() == want_best).all() and (selfsum.cpu().numpy() == want_self).all()
     assert (sim.cpu().numpy() == want_sim).all()
+
+
+# ---- query-vs-database (rectangular) -------------------------------------------------------
+@pytest.mark.parametrize("mode", ["local", "global"])
+def test_query_vs_database_scores(mode):
+    rng = np.random.default_rng(31)
+    fam = _related(rng, 4, 8, 50, 400)
+    rng.shuffle(fam)
+    q, d = fam[:7], fam[7:] + [_rand(rng, n) for n in (1, 33, 700)]
+    res = domain_pair_scores(q, database=d, mode=mode)
+    cm = 0 if mode == "local" else 1
+    full = oracle.all_pairs(q + d, mode=cm)
+    assert res.scores.shape == (len(q), len(d))
+    assert (res.scores == full[: len(q), len(q):]).all()
+    assert res.plan["total_pairs"] == len(q) * len(d) + len(q) + len(d)
+    assert len(res.db_index) == len(d)
+
+
+@pytest.mark.parametrize("same_type_only", [True, False])
+def test_query_vs_database_bgc_similarity(af293, ks_records, same_type_only):
+    col = _af293_collection(af293, ks_records)
+    ids = list(col.bgcs)
+    qcol, dcol = type(col)(), type(col)()
+    for k, b in enumerate(ids):
+        (qcol if k % 5 == 0 else dcol).bgcs[b] = col.bgcs[b]
+    res = bgc_similarity(qcol, database=dcol, same_type_only=same_type_only)
+    qb, db = extract(qcol), extract(dcol)
+    seqs = qb.sequences + db.sequences
+    names = list(dict.fromkeys(qb.type_names + db.type_names))
+    types = np.array([names.index(r.type_key) for r in qb.records + db.records])
+    Bq, Bd = len(qb.bgc_ids), len(db.bgc_ids)
+    bgcs = np.concatenate([qb.bgc_of_seq, db.bgc_of_seq + Bq])
+    scores = oracle.all_pairs(seqs)
+    # cross semantics: same-side pairs do not exist (except self)
+    side = np.arange(len(seqs)) >= len(qb)
+    masked = np.where((side[:, None] != side[None, :]) | np.eye(len(seqs), dtype=bool), scores, 0)
+    sim, best, selfs, _ = oracle.bgc_similarity_np(masked, bgcs, types, Bq + Bd, same_type_only=same_type_only)
+    assert res.bgc_ids == qb.bgc_ids and res.db_bgc_ids == db.bgc_ids
+    assert (res.best == best[:Bq, Bq:]).all() and (res.best_db == best[Bq:, :Bq]).all()
+    assert (res.self_score == selfs[:Bq]).all() and (res.db_self_score == selfs[Bq:]).all()
+    assert (res.sim == sim[:Bq, Bq:]).all()
+
+
+def test_cli_end_to_end(tmp_path, ks_records, af293):
+    """The --comparative-style entry point on the reference's own KS fixture."""
+    from bgclib_b200 import cli
+    fa = tmp_path / "all_KS_domains.fasta"
+    with open(fa, "w") as f:
+        for r in ks_records:
+            f.write(">" + r["identifier"] + "\n")
+            s = r["sequence"]
+            f.write("\n".join(s[i:i + 80] for i in range(0, len(s), 80)) + "\n")
+    assert cli.main(["--fasta", str(fa), "--out", str(tmp_path / "af293"), "--domain-scores"]) == 0
+    rows = (tmp_path / "af293.bgc_similarity.tsv").read_text().splitlines()
+    ids = rows[0].split("\t")[1:]
+    assert ids == list(dict.fromkeys(r["bgc"] for r in ks_records))
+    sim = np.array([[float(x) for x in r.split("\t")[1:]] for r in rows[1:]])
+    seqs = [r["sequence"] for r in ks_records]
+    bgc_of = np.array([ids.index(r["bgc"]) for r in ks_records])
+    want, _, _, _ = oracle.bgc_similarity_np(oracle.all_pairs(seqs), bgc_of, np.zeros(15, int), len(ids))
+    assert (sim == want).all()
+    assert (np.load(tmp_path / "af293.domain_scores.npy") == oracle.all_pairs(seqs)).all()
+    # query-vs-database through the CLI
+    assert cli.main(["--fasta", str(fa), "--db-fasta", str(fa), "--out", str(tmp_path / "x")]) == 0

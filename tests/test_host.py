@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     lib = eng.load_library()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.bgca_version() == 100
+    assert lib.bgca_version() == 101
 
 
 def test_no_device_fails_loudly():
@@ -213,3 +213,76 @@ def test_systolic_stream_of_subjects(local):
             got = systolic_stream(q.tolist(), [s.tolist() for s in subjects], sub, -12, -1, local, G, K)
             want = [oracle.score(q, s, mode=0 if local else 1) for s in subjects]
             assert got == want
+
+
+def test_planner_query_vs_database():
+    """cross_only: every query x database pair exactly once (+ one self pair per sequence)."""
+    rng = np.random.default_rng(3)
+    # sorted order = (type, role, length)
+    types, roles, lens = [], [], []
+    for t in range(3):
+        for role, cnt in ((0, int(rng.integers(0, 9))), (1, int(rng.integers(0, 40)))):
+            types += [t] * cnt
+            roles += [role] * cnt
+            lens += sorted(rng.integers(40, 500, size=cnt).tolist())
+    types, roles, lens = (np.asarray(x, np.int32) for x in (types, roles, lens))
+    n = len(lens)
+    for same_type in (True, False):
+        if not same_type:       # one block: re-sort by (role, length)
+            o = np.lexsort((lens, roles))
+            ty, ro, le = types[o], roles[o], lens[o]
+        else:
+            ty, ro, le = types, roles, lens
+        seen = []
+        for r in range(2):
+            tiles, info = plan_host(le, ty, ro, same_type_only=same_type, cross_only=True, rank=r, world=2)
+            for t in tiles:
+                for s in range(t["s_begin"], t["s_end"]):
+                    for q in (t["qa"], t["qb"]):
+                        if q < 0 or s < q:
+                            continue
+                        if q == s or ro[q] != ro[s]:          # what emit_pair keeps in cross mode
+                            seen.append((q, s))
+        want = {(i, i) for i in range(n)}
+        want |= {(i, j) for i in range(n) for j in range(i + 1, n)
+                 if ro[i] != ro[j] and (not same_type or ty[i] == ty[j])}
+        assert len(seen) == len(set(seen)) and set(seen) == want
+        assert info["total_pairs"] == len(want)
+    # a (type, role, length) order planned as ONE block would silently drop queries: refused
+    with pytest.raises(ValueError, match="queries-first"):
+        plan_host(lens, types, roles, same_type_only=False, cross_only=True)
+
+
+def test_cli_fasta_reader_and_headers(tmp_path, ks_records):
+    from bgclib_b200 import cli
+    fa = tmp_path / "d.fasta"
+    lines = []
+    for r in ks_records[:3]:
+        lines.append(">" + r["identifier"])
+        s = r["sequence"]
+        lines += [s[i:i + 80].lower() if i == 0 else s[i:i + 80] for i in range(0, len(s), 80)]
+        lines.append("")
+    lines += [">" + ks_records[0]["identifier"], "AAAA"]          # repeated header: dropped
+    fa.write_text("\n".join(lines) + "\n")
+    recs = cli.read_fasta(fa)
+    assert [h for h, _ in recs] == [r["identifier"] for r in ks_records[:3]]
+    assert [s for _, s in recs] == [r["sequence"] for r in ks_records[:3]]
+    assert cli.parse_domain_header(ks_records[0]["identifier"]) == \
+        ("CM000170.1.region002", "CM000170.1.region002~L0+CDS9", "KS")
+    assert cli.parse_domain_header("x~L0+CDS1_T/ACP12 ProteinId:a GeneId:")[2] == "T/ACP"
+    b = cli.batch_from_fasta(fa)
+    assert b.bgc_ids == [r["bgc"] for r in ks_records[:3]] and b.type_names == ["KS"]
+    alias = tmp_path / "alias.tsv"
+    alias.write_text("# c\nketoacyl-synt\tKS\tPfam\n\nAMP-binding\tA\n")
+    assert cli.read_alias_tsv(alias) == {"ketoacyl-synt": "KS", "AMP-binding": "A"}
+
+
+def test_domain_batch_round_trips_through_disk(tmp_path):
+    spec = {"b1": [("b1~L0+CDS1", "ACDEFGHIKLMNPQRSTVWY" * 3, [("ketoacyl-synt", "KS", 0, 30), ("x", "", 30, 55)])],
+            "b2": [("b2~L0+CDS1", "WWWWYYYY" * 5, [("PP-binding", "T/ACP", 2, 38)])]}
+    b = extract(build_collection(spec))
+    b.save(tmp_path / "batch.npz")
+    from bgclib_b200 import DomainBatch
+    c = DomainBatch.load(tmp_path / "batch.npz")
+    assert c.sequences == b.sequences and c.records == b.records and c.bgc_ids == b.bgc_ids
+    assert (c.type_of_seq == b.type_of_seq).all() and (c.bgc_of_seq == b.bgc_of_seq).all()
