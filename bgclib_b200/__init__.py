@@ -4,8 +4,8 @@ similarity.  Hand-written sm_100a CUDA behind a C ABI (include/bgca.h);
 PyTorch only carries device memory, streams and torch.distributed.
 """
 from .alphabet import ALPHABET, BLOSUM62  # noqa: F401
-from .api import (BGCSimilarity, DomainPairScores, attach, bgc_similarity,  # noqa: F401
-                  domain_pair_scores, get_engine)
+from .api import (BGCSimilarity, DomainPairScores, DomainPairStats, attach, bgc_similarity,  # noqa: F401
+                  domain_pair_scores, domain_pair_stats, get_engine)
 from .engine import Engine, dpx_probe, load_library, plan_host  # noqa: F401
 from .extract import DomainBatch, DomainRecord, extract  # noqa: F401
 

@@ -23,7 +23,7 @@ from typing import List, Optional
 
 import numpy as np
 
-from .engine import Engine, MODE_LOCAL, resolve_mode
+from .engine import ALNSTAT_DTYPE, Engine, MODE_LOCAL, resolve_mode
 from .extract import DomainBatch, DomainRecord, extract
 
 _ENGINES = {}
@@ -230,6 +230,61 @@ def _bgc_similarity_cross(q: DomainBatch, d: DomainBatch, matrix, open_gap_score
                          list(d.bgc_ids), selfsum[Bq:], best_dq)
 
 
+@dataclass
+class DomainPairStats:
+    stats: np.ndarray               # structured [npairs]: score, identities, columns, q_start, q_end,
+                                    # s_start, s_end, gaps (int32 each; bgca_alnstats, include/bgca.h)
+    pairs: np.ndarray               # int32 [npairs, 2]: (query, subject) positions in ``index``
+    index: List[DomainRecord]
+
+    @property
+    def identity(self) -> np.ndarray:
+        """identities / alignment columns (0 for an empty local alignment)."""
+        c = self.stats["columns"].astype(np.float64)
+        return np.divide(self.stats["identities"], c, out=np.zeros_like(c), where=c > 0)
+
+
+def domain_pair_stats(source, pairs=None, *, mode="local", matrix="BLOSUM62", open_gap_score=-12,
+                      extend_gap_score=-1, unit="domain", cbp_only=True, alias=None, domain_types=None,
+                      device=None) -> DomainPairStats:
+    """Alignment-derived statistics WITHOUT traceback (identities, alignment length, start/end
+    coordinates, gap columns) for selected domain pairs — what a BiG-SCAPE-style distance on the
+    same domains needs (the reference holds no such code).
+
+    ``pairs``: int array [npairs, 2] of (query, subject) positions in the extraction order;
+    default = every pair i < j.  The alignment described for a pair is the lexicographic maximum
+    of (score, identities, -columns, q_start, s_start, -s_end, -q_end) over all alignments in
+    ``mode`` (include/bgca.h, bgca_pair_stats), so ``score`` equals ``domain_pair_scores``' value.
+    Coordinates index the domain sequence (0-based, end-exclusive, like ali_from/ali_to,
+    BGClib/BGClib.py:3222-3241)."""
+    batch = _as_batch(source, unit, cbp_only, alias, domain_types)
+    n = len(batch)
+    if n == 0:
+        raise ValueError("no domain sequences selected")
+    if pairs is None:
+        iu = np.triu_indices(n, k=1)
+        pairs = np.stack(iu, axis=1)
+    pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+    if pairs.size and (pairs.min() < 0 or pairs.max() >= n):
+        raise ValueError("pairs: index out of range")
+    eng = get_engine(device)
+    eng.set_scoring(matrix, open_gap_score, extend_gap_score, mode)
+    eng.pack(batch.sequences)
+    dist, rank, world = _dist()
+    if dist is None:
+        out = eng.pair_stats(pairs[:, 0].copy(), pairs[:, 1].copy())
+    else:
+        # pairs are independent: rank r takes pairs r, r+world, ...; one all-reduce(sum) over the
+        # zero-initialised record table puts every record on every rank
+        out = eng.torch.zeros((len(pairs), len(ALNSTAT_DTYPE.names)), dtype=eng.torch.int32, device=eng.tdev)
+        mine = np.arange(rank, len(pairs), world)
+        if len(mine):
+            out[eng.torch.as_tensor(mine, device=eng.tdev)] = eng.pair_stats(pairs[mine, 0].copy(), pairs[mine, 1].copy())
+        dist.all_reduce(out, op=dist.ReduceOp.SUM)
+    stats = np.ascontiguousarray(out.cpu().numpy()).view(ALNSTAT_DTYPE).reshape(-1)
+    return DomainPairStats(stats, pairs, batch.records)
+
+
 def attach(collection_cls=None):
     """Adds ``domain_pair_scores`` / ``similarity_matrix`` as methods of the
     reference's BGCCollection (BGClib/BGClib.py:750) — state is NOT stored on
@@ -238,4 +293,5 @@ def attach(collection_cls=None):
         from BGClib import BGCCollection as collection_cls   # the real reference, if importable
     collection_cls.domain_pair_scores = lambda self, **kw: domain_pair_scores(self, **kw)
     collection_cls.similarity_matrix = lambda self, **kw: bgc_similarity(self, **kw)
+    collection_cls.domain_pair_stats = lambda self, pairs=None, **kw: domain_pair_stats(self, pairs, **kw)
     return collection_cls

@@ -28,6 +28,7 @@ CFLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--cud
 # (object name, source, extra defines)
 UNITS = [("bgca_api.o", "bgca_api.cu", []),
          ("pack_reduce.o", "pack_reduce.cu", []),
+         ("stats.o", "stats.cu", []),
          ("dpx_probe.o", "dpx_probe.cu", [])]
 for g in (8, 16, 32):
     for m in (0, 1):

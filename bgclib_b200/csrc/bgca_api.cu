@@ -294,6 +294,7 @@ struct bgca_engine {
     DevBuf<unsigned long long> d_err;
     DevBuf<bgca_tile> d_tiles;
     DevBuf<int2> d_scratch;
+    DevBuf<uint4> d_scratch_st;
     // plan
     std::vector<bgca_tile> tiles;
     bgca_plan_info plan_info{};
@@ -351,7 +352,7 @@ int bgca_destroy(bgca_engine *e)
     e->d_ascii.release(); e->d_codes.release(); e->d_offsets_orig.release(); e->d_order.release();
     e->d_len.release(); e->d_type.release(); e->d_bgc.release(); e->d_bgc_start.release();
     e->d_bgc_doms.release(); e->d_counters.release(); e->d_pq.release(); e->d_ps.release();
-    e->d_seq_off.release(); e->d_err.release(); e->d_tiles.release(); e->d_scratch.release();
+    e->d_seq_off.release(); e->d_err.release(); e->d_tiles.release(); e->d_scratch.release(); e->d_scratch_st.release();
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
@@ -706,6 +707,32 @@ int bgca_score(bgca_engine *e, int32_t *scores, int32_t *rowbest, int32_t *selfs
     return BGCA_OK;
 }
 
+// ORIGINAL-space device pair lists -> SORTED-space lists in e->d_pq / e->d_ps (lists are small
+// on these explicit-pair paths, so the translation runs on the host)
+static int stage_pair_list(bgca_engine *e, const int32_t *pi, const int32_t *pj, int64_t npairs,
+                           int max_len_allowed, const char *who, cudaStream_t st)
+{
+    std::vector<int32_t> hi(npairs), hj(npairs);
+    CUDA_TRY(cudaMemcpyAsync(hi.data(), pi, sizeof(int32_t) * npairs, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(hj.data(), pj, sizeof(int32_t) * npairs, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int64_t k = 0; k < npairs; ++k) {
+        if (hi[k] < 0 || hi[k] >= e->n || hj[k] < 0 || hj[k] >= e->n)
+            return fail(BGCA_ERR_INVALID, std::string(who) + ": index out of range");
+        hi[k] = e->inv_order[hi[k]];
+        hj[k] = e->inv_order[hj[k]];
+        if (e->len[hi[k]] > max_len_allowed || e->len[hj[k]] > max_len_allowed)
+            return fail(BGCA_ERR_RANGE, std::string(who) + ": sequence longer than " +
+                                            std::to_string(max_len_allowed) + " residues");
+    }
+    CUDA_TRY(e->d_pq.reserve(npairs));
+    CUDA_TRY(e->d_ps.reserve(npairs));
+    CUDA_TRY(cudaMemcpyAsync(e->d_pq.p, hi.data(), sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->d_ps.p, hj.data(), sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return BGCA_OK;
+}
+
 int bgca_score_pairs32(bgca_engine *e, const int32_t *pi, const int32_t *pj, int64_t npairs,
                        int32_t *out, void *stream)
 {
@@ -714,26 +741,37 @@ int bgca_score_pairs32(bgca_engine *e, const int32_t *pi, const int32_t *pj, int
     if (npairs == 0) return BGCA_OK;
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(e->device));
-    // translate ORIGINAL indices to sorted space on the host (lists are small on this path)
-    std::vector<int32_t> hi(npairs), hj(npairs);
-    CUDA_TRY(cudaMemcpyAsync(hi.data(), pi, sizeof(int32_t) * npairs, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(hj.data(), pj, sizeof(int32_t) * npairs, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    for (int64_t k = 0; k < npairs; ++k) {
-        if (hi[k] < 0 || hi[k] >= e->n || hj[k] < 0 || hj[k] >= e->n)
-            return fail(BGCA_ERR_INVALID, "bgca_score_pairs32: index out of range");
-        hi[k] = e->inv_order[hi[k]];
-        hj[k] = e->inv_order[hj[k]];
-    }
-    CUDA_TRY(e->d_pq.reserve(npairs));
-    CUDA_TRY(e->d_ps.reserve(npairs));
-    CUDA_TRY(cudaMemcpyAsync(e->d_pq.p, hi.data(), sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(e->d_ps.p, hj.data(), sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    int rc = stage_pair_list(e, pi, pj, npairs, 65535, "bgca_score_pairs32", st);
+    if (rc != BGCA_OK) return rc;
     ScoreParams p;
     fill_params(e, p, nullptr, nullptr, nullptr, 0);
     e->last_launches = 0;
     return run_s32_pairs(e, p, e->d_pq.p, e->d_ps.p, npairs, out, st);
+}
+
+int bgca_pair_stats(bgca_engine *e, const int32_t *pi, const int32_t *pj, int64_t npairs,
+                    bgca_alnstats *out, void *stream)
+{
+    if (!e || !e->packed || !e->scoring_set) return fail(BGCA_ERR_INVALID, "bgca_pair_stats: pack and set scoring first");
+    if (!pi || !pj || !out || npairs < 0) return fail(BGCA_ERR_INVALID, "bgca_pair_stats: bad arguments");
+    if (npairs == 0) return BGCA_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(e->device));
+    int rc = stage_pair_list(e, pi, pj, npairs, 32767, "bgca_pair_stats", st);
+    if (rc != BGCA_OK) return rc;
+    ScoreParams p;
+    fill_params(e, p, nullptr, nullptr, nullptr, 0);
+    int max_len = 0;
+    for (int r = 0; r < e->n; ++r) max_len = std::max(max_len, e->len[r]);
+    const int warps_per_cta = CTA_THREADS / 32;
+    int grid = e->n_sm * 4;
+    if ((long long)grid * warps_per_cta > npairs)
+        grid = (int)std::max<long long>(1, (npairs + warps_per_cta - 1) / warps_per_cta);
+    const int stride = (max_len + 3) & ~3;
+    CUDA_TRY(e->d_scratch_st.reserve((size_t)grid * warps_per_cta * 2 * stride));
+    CUDA_TRY(launch_stats(e->mode, p, e->d_pq.p, e->d_ps.p, npairs, e->d_scratch_st.p, stride, out, grid, st));
+    e->last_launches = 1;
+    return BGCA_OK;
 }
 
 int bgca_reduce_bgc(bgca_engine *e, const int32_t *rowbest, const int32_t *selfsc, int64_t *best,

@@ -22,6 +22,11 @@ cudaError_t launch_s32(int mode, const ScoreParams &p, const int32_t *pq, const 
                        long long npairs, int2 *scratch, int scratch_stride, int32_t *out_list,
                        int grid, cudaStream_t st);
 
+// K7 (stats.cu)
+cudaError_t launch_stats(int mode, const ScoreParams &p, const int32_t *pq, const int32_t *ps,
+                         long long npairs, uint4 *scratch, int scratch_stride, bgca_alnstats *out,
+                         int grid, cudaStream_t st);
+
 // K1 / K5 kernels (pack_reduce.cu)
 cudaError_t launch_pack(const uint8_t *ascii, const int64_t *offsets_orig, const int32_t *order,
                         const uint32_t *seq_off, const int32_t *seq_len, int32_t n, uint8_t *codes,

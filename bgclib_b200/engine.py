@@ -32,7 +32,7 @@ _lib = None
 EXPORTED_SYMBOLS = (
     "bgca_version", "bgca_last_error", "bgca_create", "bgca_destroy", "bgca_set_scoring",
     "bgca_pack", "bgca_packed_bytes", "bgca_get_packed", "bgca_plan", "bgca_plan_host",
-    "bgca_score", "bgca_score_pairs32", "bgca_reduce_bgc", "bgca_score_all_host",
+    "bgca_score", "bgca_score_pairs32", "bgca_pair_stats", "bgca_reduce_bgc", "bgca_score_all_host",
     "bgca_last_launches", "bgca_last_dp_ms", "bgca_dpx_probe",
 )
 
@@ -80,6 +80,7 @@ def load_library():
                                    P(i64), P(PlanInfo)]
     lib.bgca_score.argtypes = [vp, vp, vp, vp, i32, vp]
     lib.bgca_score_pairs32.argtypes = [vp, vp, vp, i64, vp, vp]
+    lib.bgca_pair_stats.argtypes = [vp, vp, vp, i64, vp, vp]
     lib.bgca_reduce_bgc.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.bgca_score_all_host.argtypes = [vp, vp, vp, i32, vp]
     lib.bgca_last_launches.argtypes = [vp]
@@ -279,6 +280,21 @@ class Engine:
                                                 self._stream()))
         return out
 
+    def pair_stats(self, pi, pj):
+        """K7: alignment statistics without traceback for pairs (query pi[p], subject pj[p]) of the
+        packed batch, ORIGINAL indices.  Returns a CUDA int32 tensor [npairs, 8] whose columns are
+        ``ALNSTAT_FIELDS`` (the bgca_alnstats record)."""
+        t = self.torch
+        pi = t.as_tensor(pi, dtype=t.int32, device=self.tdev).contiguous()
+        pj = t.as_tensor(pj, dtype=t.int32, device=self.tdev).contiguous()
+        if pi.shape != pj.shape or pi.dim() != 1:
+            raise ValueError("pi and pj must be 1-D and of equal length")
+        out = t.zeros((pi.numel(), len(ALNSTAT_FIELDS)), dtype=t.int32, device=self.tdev)
+        with t.cuda.device(self.tdev):
+            _check(self._lib.bgca_pair_stats(self._h, _t_ptr(pi), _t_ptr(pj), pi.numel(), _t_ptr(out),
+                                             self._stream()))
+        return out
+
     def reduce_bgc(self, rowbest, selfsc):
         t = self.torch
         B = self.n_bgc
@@ -312,6 +328,10 @@ class Engine:
         ms = ctypes.c_float(0)
         _check(self._lib.bgca_last_dp_ms(self._h, ctypes.byref(ms)))
         return float(ms.value)
+
+
+ALNSTAT_FIELDS = ("score", "identities", "columns", "q_start", "q_end", "s_start", "s_end", "gaps")
+ALNSTAT_DTYPE = np.dtype([(k, np.int32) for k in ALNSTAT_FIELDS])
 
 
 def dpx_probe(device: int = 0) -> dict:

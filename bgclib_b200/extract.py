@@ -76,6 +76,87 @@ class DomainBatch:
                    z["type_of_seq"].astype(np.int32))
 
 
+@dataclass(frozen=True)
+class DomainSpan:
+    """A domain as the aligner sees it: either one BGCDomain or the merge of consecutive
+    fragments of a split domain.  Duck-types the BGCDomain attributes ``extract`` reads."""
+    protein: object
+    ID: str
+    alias: str
+    ali_from: int
+    ali_to: int
+    hmm_from: int
+    hmm_to: int
+    score: float
+    n_fragments: int = 1
+
+    def get_sequence(self) -> str:
+        return self.protein.sequence[self.ali_from:self.ali_to]
+
+
+def split_domain_groups(domain_list: Sequence) -> List[List[int]]:
+    """Positions (in ``domain_list``) of the fragment runs that the reference's
+    ``fix_core_split_domains`` (BGCtoolkit.py:575-687) stitches into one domain: consecutive
+    domains with the same ID whose HMM coordinates advance (prev.hmm_to < next.hmm_from).
+    Restated with the reference's exact scan, including its edge behaviour: a run is only opened
+    by the FIRST domain of an ID stretch (look-ahead at :601-604), a fragment that does not
+    advance is skipped while the run stays open (:609-611), and a run still open when the last
+    domain has the same ID but does not advance is dropped (:618-621)."""
+    groups: List[List[int]] = []
+    n = len(domain_list)
+    if n == 0:
+        return groups
+    run: List[int] = []
+    current_id = ""                      # the reference starts from the empty string (:591)
+    for k in range(n - 1):
+        d = domain_list[k]
+        if current_id != d.ID:
+            if run:
+                groups.append(run)
+            run = []
+            nxt = domain_list[k + 1]
+            if d.ID == nxt.ID and d.hmm_to < nxt.hmm_from:
+                run = [k]
+            current_id = d.ID
+        elif run:
+            if domain_list[run[-1]].hmm_to < d.hmm_from:
+                run.append(k)
+    last = domain_list[n - 1]
+    if current_id != last.ID:
+        if run:
+            groups.append(run)
+    elif run:
+        if domain_list[run[-1]].hmm_to < last.hmm_from:
+            run.append(n - 1)
+            groups.append(run)
+    return groups
+
+
+def merged_domain_view(protein) -> List[DomainSpan]:
+    """``protein.domain_list`` as it would read after ``fix_core_split_domains``
+    (BGCtoolkit.py:662-687) — computed on the side, the protein is NOT modified: per run the
+    fragments are removed, the merged domain (first.ali_from .. last.ali_to, first.hmm_from ..
+    last.hmm_to, score = sum of the parts) is appended and the list is re-sorted by ali_from
+    (stable), run after run, as the reference does."""
+    doms = list(protein.domain_list)
+    view = [DomainSpan(protein, d.ID, getattr(d, "alias", ""), d.ali_from, d.ali_to, getattr(d, "hmm_from", 0),
+                       getattr(d, "hmm_to", 0), getattr(d, "score", 0)) for d in doms]
+    spans = list(view)
+    for run in split_domain_groups(doms):
+        parts = [view[k] for k in run]
+        first, last = parts[0], parts[-1]
+        merged = DomainSpan(protein, first.ID, first.alias, first.ali_from, last.ali_to, first.hmm_from,
+                            last.hmm_to, sum(x.score for x in parts), len(parts))
+        for x in parts:
+            for pos, y in enumerate(spans):     # list.remove by identity, like the reference's objects
+                if y is x:
+                    del spans[pos]
+                    break
+        spans.append(merged)
+        spans.sort(key=lambda x: x.ali_from)
+    return spans
+
+
 def type_key(domain, alias: Optional[dict]) -> str:
     if alias:
         try:
@@ -115,7 +196,7 @@ def _bgc_proteins(bgc, cbp_only: bool):
 
 
 def extract(source, *, unit: str = "domain", cbp_only: bool = True, alias: Optional[dict] = None,
-            domain_types: Optional[Iterable[str]] = None) -> DomainBatch:
+            domain_types: Optional[Iterable[str]] = None, merge_split_domains: bool = False) -> DomainBatch:
     """Flatten ``source`` into a DomainBatch.
 
     source: BGCCollection | BGC | ProteinCollection | iterable of BGC / BGCProtein /
@@ -125,6 +206,9 @@ def extract(source, *, unit: str = "domain", cbp_only: bool = True, alias: Optio
                         reference's own domain FASTA exports load back as,
                         e.g. examples/all_KS_domains.fasta).
     domain_types: optional set of type keys to keep (e.g. {"KS"}).
+    merge_split_domains: align the domains a protein would have after the reference's
+            ``fix_core_split_domains`` post-processing (BGCtoolkit.py:575-687) without running it
+            on (and so without modifying) the objects — see ``merged_domain_view``.
     """
     if unit not in ("domain", "protein"):
         raise ValueError("unit must be 'domain' or 'protein'")
@@ -169,7 +253,7 @@ def extract(source, *, unit: str = "domain", cbp_only: bool = True, alias: Optio
             tkey = getattr(p, "protein_type", "") or "protein"
             add(p.sequence, name, p.identifier, "", tkey, 0, len(p.sequence))
             return
-        for d in p.domain_list:
+        for d in (merged_domain_view(p) if merge_split_domains else p.domain_list):
             add(d.get_sequence(), name, p.identifier, d.ID, type_key(d, alias), d.ali_from, d.ali_to)
 
     def add_bgc(bgc):

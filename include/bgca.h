@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define BGCA_VERSION 101
+#define BGCA_VERSION 102
 
 #define BGCA_MODE_LOCAL 0  /* Smith-Waterman/Gotoh, result = best cell, >= 0        */
 #define BGCA_MODE_GLOBAL 1 /* Needleman-Wunsch/Gotoh, end gaps cost like internal   */
@@ -142,6 +142,23 @@ int bgca_score(bgca_engine *e, int32_t *scores, int32_t *rowbest, int32_t *selfs
  * out[p] = s(pi[p], pj[p]); pi/pj/out are device pointers, ORIGINAL indices. */
 int bgca_score_pairs32(bgca_engine *e, const int32_t *pi, const int32_t *pj, int64_t npairs,
                        int32_t *out, void *stream);
+
+/* K7 — alignment statistics without traceback for an explicit pair list (SURVEY.md §8f-1;
+ * the quantity a BiG-SCAPE-style distance on the same domains needs; the reference has no
+ * such code).  Query = sequence pi[p], subject = sequence pj[p] (device pointers, ORIGINAL
+ * indices); out is a device array of npairs records.  The alignment described is the
+ * lexicographic maximum of (score, identities, -columns, q_start, s_start, -s_end, -q_end)
+ * over all alignments of the affine-gap model in the engine's mode; score equals what
+ * bgca_score() reports for the pair.  Coordinates are 0-based and end-exclusive like
+ * BGCDomain.ali_from/ali_to (BGClib/BGClib.py:3222-3241); the empty local alignment
+ * (score 0) has columns 0 and all four coordinates -1.  gaps = gap columns
+ * (2*columns - query span - subject span); aligned residue pairs = columns - gaps.
+ * Sequences longer than 32767 residues -> BGCA_ERR_RANGE. */
+typedef struct bgca_alnstats {
+    int32_t score, identities, columns, q_start, q_end, s_start, s_end, gaps;
+} bgca_alnstats;
+int bgca_pair_stats(bgca_engine *e, const int32_t *pi, const int32_t *pj, int64_t npairs,
+                    bgca_alnstats *out, void *stream);
 
 /* K5 second stage (after ranks combined rowbest/selfsc with max):
  *   best[a,b] = sum_{d in a} rowbest[d,b]   int64[n_bgc*n_bgc]

@@ -11,5 +11,5 @@ What pins this oracle instead is stated in ``oracle/gotoh_oracle.c``.
 """
 from .cbind import (  # noqa: F401
     ALPHABET, BLOSUM62, MODE_GLOBAL, MODE_LOCAL, all_pairs, bgc_similarity_np,
-    encode, load, num_threads, pair_list, score, score_3state,
+    STATS_DTYPE, encode, load, num_threads, pair_list, score, score_3state, stats_list,
 )

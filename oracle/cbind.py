@@ -82,6 +82,9 @@ def load():
     lib.bgco_pair_list.argtypes = [u8p, i64p, i32, i32p, i32p, ctypes.c_int64, i8p, i32, i32,
                                    i32, i32p, i32]
     lib.bgco_pair_list.restype = None
+    lib.bgco_stats_list.argtypes = [u8p, i64p, i32, i32p, i32p, ctypes.c_int64, i8p, i32, i32, i32,
+                                    ctypes.c_void_p, i32]
+    lib.bgco_stats_list.restype = i32
     lib.bgco_num_threads.argtypes = []
     lib.bgco_num_threads.restype = i32
     _LIB = lib
@@ -161,6 +164,29 @@ def pair_list(seqs, pi, pj, *, mode=MODE_LOCAL, sub=BLOSUM62, open_gap=-12, exte
                        _p(pi, ctypes.c_int32), _p(pj, ctypes.c_int32), len(pi),
                        _p(sub, ctypes.c_int8), open_gap, extend_gap, mode,
                        _p(out, ctypes.c_int32), nthreads)
+    return out
+
+
+STATS_DTYPE = np.dtype([(k, np.int32) for k in ("score", "identities", "columns", "q_start", "q_end",
+                                                "s_start", "s_end", "gaps")])
+
+
+def stats_list(seqs, pi, pj, *, mode=MODE_LOCAL, sub=BLOSUM62, open_gap=-12, extend_gap=-1,
+               nthreads=0) -> np.ndarray:
+    """Alignment statistics without traceback for an explicit pair list (query = seqs[pi[p]],
+    subject = seqs[pj[p]]); structured array with the fields of ``bgco_stats``."""
+    lib = load()
+    codes, offsets = _pack(seqs)
+    pi = np.ascontiguousarray(pi, dtype=np.int32)
+    pj = np.ascontiguousarray(pj, dtype=np.int32)
+    out = np.zeros(len(pi), dtype=STATS_DTYPE)
+    sub = np.ascontiguousarray(sub, dtype=np.int8)
+    rc = lib.bgco_stats_list(_p(codes, ctypes.c_uint8), _p(offsets, ctypes.c_int64), len(offsets) - 1,
+                             _p(pi, ctypes.c_int32), _p(pj, ctypes.c_int32), len(pi),
+                             _p(sub, ctypes.c_int8), open_gap, extend_gap, mode,
+                             out.ctypes.data_as(ctypes.c_void_p), nthreads)
+    if rc != 0:
+        raise ValueError("stats: sequence lengths must be in 1..32767")
     return out
 
 

@@ -203,3 +203,125 @@ int32_t bgco_num_threads(void)
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Alignment statistics without traceback (the reference has no such code —
+ * this is this build's definition, DESIGN.md "K7").
+ *
+ * Every alignment A of the affine-gap model (local: any monotone path between two cells,
+ * including the empty one; global: corner to corner) has the additive value
+ *     v(A) = (score, identities, -columns)
+ * (identities = columns whose two letters are equal, columns = alignment length).  The
+ * alignment reported for a pair is the lexicographic maximum of
+ *     (score, identities, -columns, q_start, s_start, -s_end, -q_end)
+ * over all alignments.  v is additive along a path and the start is fixed at the path's
+ * origin, so the maximum is computed exactly by the Gotoh recurrence over tuples; no
+ * traceback, no dependence on evaluation order.  Coordinates are 0-based, end-exclusive
+ * (the convention of BGCDomain.ali_from/ali_to, BGClib/BGClib.py:3222-3241); the empty
+ * local alignment reports -1 for all four.
+ *
+ * Tuple encoding (shared with the CUDA kernel so that both sides state the same order):
+ * key = score * 2^32 + identities * 2^16 + (65535 - columns), pay = q_start * 2^16 + s_start.
+ * Needs len_a, len_b <= 32767.
+ */
+typedef struct bgco_stats {
+    int32_t score, identities, columns, q_start, q_end, s_start, s_end, gaps;
+} bgco_stats;
+
+typedef struct { int64_t k; uint32_t p; } tup;
+
+static inline int tup_gt(tup a, tup b) { return a.k > b.k || (a.k == b.k && a.p > b.p); }
+static inline tup tup_max(tup a, tup b) { return tup_gt(b, a) ? b : a; }
+static inline tup tup_add(tup a, int32_t score, int32_t ident)
+{
+    a.k += (int64_t)score * 4294967296LL + (int64_t)ident * 65536 - 1;   /* one more column */
+    return a;
+}
+static inline tup tup_zero(int32_t i, int32_t j)   /* empty alignment at DP corner (i, j) */
+{
+    tup z = {65535, ((uint32_t)i << 16) | (uint32_t)j};
+    return z;
+}
+
+int32_t bgco_stats_pair(const uint8_t *a, int32_t la, const uint8_t *b, int32_t lb,
+                        const int8_t *sub, int32_t open, int32_t extend, int32_t mode,
+                        bgco_stats *out)
+{
+    if (la <= 0 || lb <= 0 || la > 32767 || lb > 32767) return -1;
+    const int local = (mode == BGCO_MODE_LOCAL);
+    const tup NEG = {(int64_t)BGCO_NEG * 4294967296LL + 65535, 0};
+    tup *H = (tup *)malloc(sizeof(tup) * 2 * (size_t)(lb + 1));
+    tup *E = H + lb + 1;   /* vertical-gap state per column, carried down the rows */
+    tup best = tup_zero(0, 0);
+    int32_t best_i = 0, best_j = 0;   /* DP corner where the best alignment ends */
+
+    H[0] = tup_zero(0, 0);
+    for (int32_t j = 1; j <= lb; ++j) {
+        if (local) H[j] = tup_zero(0, j);
+        else H[j] = tup_add(j == 1 ? tup_zero(0, 0) : H[j - 1], j == 1 ? open : extend, 0);
+        E[j] = NEG;
+    }
+    for (int32_t i = 1; i <= la; ++i) {
+        const int8_t *srow = sub + (size_t)a[i - 1] * BGCO_NSYM;
+        tup diag = H[0];
+        tup left = local ? tup_zero(i, 0) : tup_add(H[0], i == 1 ? open : extend, 0);
+        tup F = NEG;
+        H[0] = left;
+        for (int32_t j = 1; j <= lb; ++j) {
+            tup e = tup_max(tup_add(E[j], extend, 0), tup_add(H[j], open, 0));
+            F = tup_max(tup_add(F, extend, 0), tup_add(left, open, 0));
+            tup h = tup_add(diag, srow[b[j - 1]], a[i - 1] == b[j - 1]);
+            h = tup_max(tup_max(h, e), F);
+            if (local) {
+                h = tup_max(h, tup_zero(i, j));
+                /* (key, start) first; then the smaller s_end, then the smaller q_end */
+                if (tup_gt(h, best) ||
+                    (h.k == best.k && h.p == best.p && (h.k & 0xFFFF) != 65535 &&
+                     (j < best_j || (j == best_j && i < best_i)))) {
+                    best = h; best_i = i; best_j = j;
+                }
+            }
+            diag = H[j];
+            H[j] = h;
+            E[j] = e;
+            left = h;
+        }
+    }
+    if (!local) { best = H[lb]; best_i = la; best_j = lb; }
+    free(H);
+    out->score = (int32_t)(best.k >> 32);
+    out->identities = (int32_t)((best.k >> 16) & 0xFFFF);
+    out->columns = 65535 - (int32_t)(best.k & 0xFFFF);
+    if (out->columns == 0) {
+        out->q_start = out->q_end = out->s_start = out->s_end = -1;
+        out->gaps = 0;
+    } else {
+        out->q_start = (int32_t)(best.p >> 16);
+        out->s_start = (int32_t)(best.p & 0xFFFF);
+        out->q_end = best_i;
+        out->s_end = best_j;
+        out->gaps = 2 * out->columns - (out->q_end - out->q_start) - (out->s_end - out->s_start);
+    }
+    return 0;
+}
+
+/* Explicit pair list: out[p] = stats(seq[pi[p]] as query, seq[pj[p]] as subject). */
+int32_t bgco_stats_list(const uint8_t *codes, const int64_t *offsets, int32_t n,
+                        const int32_t *pi, const int32_t *pj, int64_t npairs,
+                        const int8_t *sub, int32_t open, int32_t extend, int32_t mode,
+                        bgco_stats *out, int32_t nthreads)
+{
+    (void)n;
+    int32_t bad = 0;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 4) reduction(| : bad)
+    for (int64_t p = 0; p < npairs; ++p) {
+        int32_t i = pi[p], j = pj[p];
+        bad |= bgco_stats_pair(codes + offsets[i], (int32_t)(offsets[i + 1] - offsets[i]),
+                               codes + offsets[j], (int32_t)(offsets[j + 1] - offsets[j]),
+                               sub, open, extend, mode, &out[p]) != 0;
+    }
+    return bad ? -1 : 0;
+}

@@ -17,6 +17,8 @@ writes
                     (examples/AfumigatusAf293.metadata.CBPs.tsv)
   ks_scores.json    oracle score matrices for the four parameter settings of
                     SURVEY.md App. B with their SHA-256 digests.
+  ks_stats.json     oracle alignment statistics (score, identities, columns, coordinates, gaps)
+                    of all 225 ordered pairs, local and global, -12/-1.
 
 The score vectors come from oracle/ (CPU restatement), not from the reference:
 the reference has no aligner (PARITY UNPINNED).
@@ -104,6 +106,17 @@ def main():
                 "matrix": m.tolist(),
             }
     (HERE / "ks_scores.json").write_text(json.dumps(out) + "\n")
+
+    # alignment statistics without traceback (oracle/gotoh_oracle.c bgco_stats_pair) for every
+    # ORDERED pair (query i, subject j) of the 15 KS domains, -12/-1
+    n = len(seqs)
+    pi, pj = np.divmod(np.arange(n * n), n)
+    stats = {"fields": list(oracle.STATS_DTYPE.names), "open": -12, "extend": -1}
+    for mode_name, mode in (("local", oracle.MODE_LOCAL), ("global", oracle.MODE_GLOBAL)):
+        st = oracle.stats_list(seqs, pi, pj, mode=mode)
+        rows = np.stack([st[k] for k in oracle.STATS_DTYPE.names], axis=1).astype("<i4")
+        stats[mode_name] = {"sha256_int32_le": hashlib.sha256(rows.tobytes()).hexdigest(), "records": rows.tolist()}
+    (HERE / "ks_stats.json").write_text(json.dumps(stats) + "\n")
     print("wrote", [p.name for p in HERE.glob("*.json")])
     for k, v in out.items():
         print(k, v["sha256_int32_le"], np.array(v["matrix"])[0].tolist())

@@ -349,3 +349,59 @@ def test_cli_end_to_end(tmp_path, ks_records, af293):
     assert (np.load(tmp_path / "af293.domain_scores.npy") == oracle.all_pairs(seqs)).all()
     # query-vs-database through the CLI
     assert cli.main(["--fasta", str(fa), "--db-fasta", str(fa), "--out", str(tmp_path / "x")]) == 0
+
+
+# ---- K7: alignment statistics without traceback --------------------------------------------
+def _stat_rows(st):
+    return np.stack([st[k] for k in oracle.STATS_DTYPE.names], axis=1)
+
+
+@pytest.mark.parametrize("mode", ["local", "global"])
+def test_stats_ks_golden(ks_records, mode):
+    import hashlib as _h
+    import json
+    from conftest import GOLDEN
+    from bgclib_b200 import domain_pair_stats
+    gold = json.loads((GOLDEN / "ks_stats.json").read_text())
+    seqs = [r["sequence"] for r in ks_records]
+    n = len(seqs)
+    pairs = np.stack(np.divmod(np.arange(n * n), n), axis=1)
+    res = domain_pair_stats(seqs, pairs, mode=mode)
+    rows = _stat_rows(res.stats).astype("<i4")
+    assert (rows == np.array(gold[mode]["records"], dtype=np.int32)).all()
+    assert _h.sha256(rows.tobytes()).hexdigest() == gold[mode]["sha256_int32_le"]
+    assert (res.identity.reshape(n, n).diagonal() == 1.0).all()
+
+
+@pytest.mark.parametrize("mode", ["local", "global"])
+@pytest.mark.parametrize("lo,hi", [(1, 12), (30, 90), (200, 300), (250, 530), (700, 1100)])
+def test_stats_random_bit_exact(mode, lo, hi):
+    """Single-pass and multi-pass (query > 256 rows) sweeps, ties, B/Z/X letters, empty alignments."""
+    from bgclib_b200 import domain_pair_stats
+    rng = np.random.default_rng(lo + 3 * hi + (mode == "global"))
+    letters = AA + "BZX" if lo < 100 else AA
+    seqs = _related(rng, 3, 5, lo, hi, letters) + [_rand(rng, rng.integers(lo, hi + 1), "WP"[k % 2]) for k in range(4)]
+    n = len(seqs)
+    pairs = np.stack(np.divmod(np.arange(n * n), n), axis=1)
+    res = domain_pair_stats(seqs, pairs, mode=mode)
+    cm = oracle.MODE_LOCAL if mode == "local" else oracle.MODE_GLOBAL
+    want = oracle.stats_list(seqs, pairs[:, 0], pairs[:, 1], mode=cm)
+    assert (_stat_rows(res.stats) == _stat_rows(want)).all()
+    assert (res.stats["score"] == domain_pair_scores(seqs, mode=mode).scores.reshape(-1)).all()
+
+
+def test_stats_other_gap_scores_and_default_pairs():
+    from bgclib_b200 import domain_pair_stats
+    rng = np.random.default_rng(77)
+    seqs = _related(rng, 2, 6, 40, 160)
+    for o, e in ((-11, -1), (-5, -2), (-3, 0), (-1, -1)):
+        res = domain_pair_stats(seqs, open_gap_score=o, extend_gap_score=e)
+        assert len(res.pairs) == len(seqs) * (len(seqs) - 1) // 2 and (res.pairs[:, 0] < res.pairs[:, 1]).all()
+        want = oracle.stats_list(seqs, res.pairs[:, 0], res.pairs[:, 1], open_gap=o, extend_gap=e)
+        assert (_stat_rows(res.stats) == _stat_rows(want)).all()
+
+
+def test_stats_rejects_sequences_beyond_32767():
+    from bgclib_b200 import domain_pair_stats
+    with pytest.raises(ValueError, match="32767"):
+        domain_pair_stats(["A" * 40000, "ACD"], [[0, 1]])

@@ -135,3 +135,63 @@ def test_bgc_similarity_restatement():
     assert sim[0, 1] == (2 + 2) / (18 + 12) and sim[0, 0] == 1.0 and sim[1, 2] == 0.0
     sim2, best2, _, _ = oracle.bgc_similarity_np(s, bgc, typ, 3, same_type_only=False)
     assert best2[0].tolist() == [18, 5, 1]
+
+
+# ---- alignment statistics without traceback (oracle/gotoh_oracle.c bgco_stats_pair) ---------
+def _s(rec):
+    return {k: int(rec[k]) for k in rec.dtype.names}
+
+
+def test_stats_three_formulations_agree_on_tiny_inputs():
+    """C packed-key H/E/F DP == Python 3-state tuple DP == enumeration of every path."""
+    from oracle import stats_py
+    rng = np.random.default_rng(5)
+    for _ in range(120):
+        a = "".join("ACDE"[i] for i in rng.integers(0, 4, int(rng.integers(1, 5))))
+        b = "".join("ACDE"[i] for i in rng.integers(0, 4, int(rng.integers(1, 5))))
+        for mode, cm in (("local", oracle.MODE_LOCAL), ("global", oracle.MODE_GLOBAL)):
+            for o, e in ((-12, -1), (-2, -1), (-1, -1), (-3, 0), (0, 0)):
+                c = _s(oracle.stats_list([a, b], [0], [1], mode=cm, open_gap=o, extend_gap=e)[0])
+                assert c == stats_py.stats_3state(a, b, mode, o, e) == stats_py.stats_bruteforce(a, b, mode, o, e)
+
+
+def test_stats_c_vs_python_on_domain_sized_inputs(ks_records):
+    from oracle import stats_py
+    seqs = [r["sequence"][:120] for r in ks_records[:4]]
+    for i, j in ((0, 1), (2, 0), (3, 3)):
+        for mode, cm in (("local", oracle.MODE_LOCAL), ("global", oracle.MODE_GLOBAL)):
+            assert _s(oracle.stats_list(seqs, [i], [j], mode=cm)[0]) == stats_py.stats_3state(seqs[i], seqs[j], mode)
+
+
+def test_stats_golden_and_properties(ks_records, ks_golden):
+    import json
+    from conftest import GOLDEN
+    gold = json.loads((GOLDEN / "ks_stats.json").read_text())
+    seqs = [r["sequence"] for r in ks_records]
+    n = len(seqs)
+    pi, pj = np.divmod(np.arange(n * n), n)
+    lens = np.array([len(s) for s in seqs])
+    for mode, cm in (("local", oracle.MODE_LOCAL), ("global", oracle.MODE_GLOBAL)):
+        st = oracle.stats_list(seqs, pi, pj, mode=cm)
+        rows = np.stack([st[k] for k in gold["fields"]], axis=1).astype("<i4")
+        assert hashlib.sha256(rows.tobytes()).hexdigest() == gold[mode]["sha256_int32_le"]
+        assert (rows == np.array(gold[mode]["records"], dtype=np.int32)).all()
+        # the score field IS the alignment score of the scoring path
+        assert (st["score"].reshape(n, n) == np.array(ks_golden[f"{mode}_12_1"]["matrix"])).all()
+        assert (st["identities"] <= st["columns"]).all() and (st["gaps"] >= 0).all()
+        assert (st["q_end"] - st["q_start"] + st["s_end"] - st["s_start"] == 2 * st["columns"] - st["gaps"]).all()
+        d = st.reshape(n, n)[np.arange(n), np.arange(n)]        # self alignment = the whole sequence
+        assert (d["identities"] == lens).all() and (d["columns"] == lens).all() and (d["gaps"] == 0).all()
+        if mode == "global":
+            assert (st["q_start"] == 0).all() and (st["q_end"] == lens[pi]).all() and (st["s_end"] == lens[pj]).all()
+    # swapping query and subject keeps the additive value (score, identities, columns)
+    loc = oracle.stats_list(seqs, pi, pj).reshape(n, n)
+    for k in ("score", "identities", "columns", "gaps"):
+        assert (loc[k] == loc[k].T).all()
+
+
+def test_stats_empty_local_alignment_and_limits():
+    st = oracle.stats_list(["WWWW", "PPPP"], [0], [1])[0]
+    assert _s(st) == dict(score=0, identities=0, columns=0, q_start=-1, q_end=-1, s_start=-1, s_end=-1, gaps=0)
+    with pytest.raises(ValueError):
+        oracle.stats_list(["A" * 32768, "A"], [0], [1])
