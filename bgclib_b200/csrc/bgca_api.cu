@@ -461,14 +461,15 @@ int bgca_pack(bgca_engine *e, const uint8_t *ascii, const int64_t *offsets, int3
     const int64_t total_ascii = offsets[n] - offsets[0];
     const uint8_t *d_src = ascii + offsets[0];
     if (!ascii_on_device) {
-        CUDA_TRY(e->d_ascii.reserve((size_t)total_ascii));
+        CUDA_TRY(e->d_ascii.reserve((size_t)total_ascii + 16));   // K1 reads whole aligned 16-byte words
         CUDA_TRY(cudaMemcpyAsync(e->d_ascii.p, ascii + offsets[0], (size_t)total_ascii,
                                  cudaMemcpyHostToDevice, st));
         d_src = e->d_ascii.p;
     }
-    std::vector<int64_t> off_rel(n + 1);
-    for (int i = 0; i <= n; ++i) off_rel[i] = offsets[i] - offsets[0];
-    CUDA_TRY(e->d_offsets_orig.reserve(n + 1));
+    // source byte offset of every SORTED sequence (relative to d_src): one gather less on the device
+    std::vector<int64_t> off_rel(n);
+    for (int r = 0; r < n; ++r) off_rel[r] = offsets[e->order[r]] - offsets[0];
+    CUDA_TRY(e->d_offsets_orig.reserve(n));
     CUDA_TRY(e->d_order.reserve(n));
     CUDA_TRY(e->d_len.reserve(n));
     CUDA_TRY(e->d_type.reserve(n));
@@ -478,7 +479,7 @@ int bgca_pack(bgca_engine *e, const uint8_t *ascii, const int64_t *offsets, int3
     CUDA_TRY(e->d_err.reserve(1));
     CUDA_TRY(e->d_bgc_start.reserve(e->bgc_start.size()));
     CUDA_TRY(e->d_bgc_doms.reserve(std::max<size_t>(e->bgc_doms.size(), 1)));
-    CUDA_TRY(cudaMemcpyAsync(e->d_offsets_orig.p, off_rel.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->d_offsets_orig.p, off_rel.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(e->d_order.p, e->order.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(e->d_len.p, e->len.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(e->d_type.p, e->type.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));

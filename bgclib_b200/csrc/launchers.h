@@ -28,7 +28,7 @@ cudaError_t launch_stats(int mode, const ScoreParams &p, const int32_t *pq, cons
                          int grid, cudaStream_t st);
 
 // K1 / K5 kernels (pack_reduce.cu)
-cudaError_t launch_pack(const uint8_t *ascii, const int64_t *offsets_orig, const int32_t *order,
+cudaError_t launch_pack(const uint8_t *ascii, const int64_t *src_off_sorted, const int32_t *order,
                         const uint32_t *seq_off, const int32_t *seq_len, int32_t n, uint8_t *codes,
                         unsigned long long *err_word, cudaStream_t st);
 cudaError_t launch_bgc_reduce(const int32_t *rowbest, const int32_t *selfsc, const int32_t *bgc_start,

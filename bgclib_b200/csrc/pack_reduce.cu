@@ -7,9 +7,19 @@ namespace bgca {
 // ---------------------------------------------------------------------------
 // K1: ASCII -> residue codes, written in SORTED order, each sequence followed by
 // at least one BGCA_PAD_CODE byte (the DP kernels read it as the end-of-subject
-// token) and padded to a 16-byte multiple.  One warp per sequence; each lane
-// encodes 16 residues and issues one 128-bit store, so the write side is
-// fully coalesced; the read side is byte loads that L1 merges into full lines.
+// token) and padded to a 16-byte multiple.
+//
+// HBM-bound by design: a lane owns one 16-byte output chunk; it fetches the (at
+// most two) 16-byte ALIGNED source words that cover its 16 residues with 128-bit
+// loads — the source strings sit at arbitrary byte offsets — realigns them with
+// funnel shifts, encodes through a 256-byte shared-memory table (letters A..Z
+// fall in 7 distinct banks: no conflicts) and issues one 128-bit store.  A warp
+// takes PACK_SEQS consecutive sorted sequences per iteration and issues all
+// their loads before using any (the unrolled first 512 bytes of each), with the
+// next iteration's metadata prefetched, so the kernel is limited by bytes in
+// flight rather than by dependent-load latency.  Only aligned words that hold
+// at least one valid residue are touched, so nothing outside the caller's
+// buffer is read.
 // Algorithmic bytes: sum(L) read + sum(roundup16(L+1)) written.
 // A letter outside the alphabet is reported through err_word =
 // (original sequence index << 32) | position, smallest wins; ~0 = no error.
@@ -28,52 +38,150 @@ __device__ __forceinline__ uint32_t encode_residue(uint32_t ch)
     }
 }
 
+constexpr int PACK_SEQS = 4;     // sequences per warp iteration
+constexpr int PACK_ROUNDS = 4;   // unrolled rounds of 32 chunks whose loads are all in flight together
+
+// One 16-byte output chunk.  Source side: five 4-byte-aligned words cover the 16 residues
+// whatever the byte offset of the string (strings sit at arbitrary offsets); only words that
+// hold at least one residue of this sequence are read, so nothing outside the caller's buffer
+// is touched.
+struct PackChunk {
+    uint32_t w[5];
+};
+
+__device__ __forceinline__ PackChunk pack_fetch(const uint8_t *src, int len, int base)
+{
+    PackChunk c;
+    const uintptr_t p = reinterpret_cast<uintptr_t>(src) + (uintptr_t)base;
+    const uintptr_t end = reinterpret_cast<uintptr_t>(src) + (uintptr_t)len;
+    const uint32_t *a = reinterpret_cast<const uint32_t *>(p & ~(uintptr_t)3);
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+        c.w[i] = (base < len && reinterpret_cast<uintptr_t>(a + i) < end) ? __ldg(a + i) : 0u;
+    return c;
+}
+
+// realign (one funnel shift per word), encode through the shared table, blank what lies past
+// the sequence with the pad code, one 128-bit store.  Returns the OR of the encoded words: a
+// set bit 7 in any byte = an illegal letter somewhere in this chunk.
+__device__ __forceinline__ uint32_t pack_emit(const PackChunk &c, const uint8_t *src, int len, int base,
+                                              uint8_t *dst, const uint8_t *lut)
+{
+    const uint32_t bits = (uint32_t)((reinterpret_cast<uintptr_t>(src) + (uintptr_t)base) & 3) * 8;
+    uint32_t out[4], bad = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t raw = __funnelshift_r(c.w[i], c.w[i + 1], bits);
+        const uint32_t c0 = lut[raw & 0xFFu], c1 = lut[(raw >> 8) & 0xFFu];
+        const uint32_t c2 = lut[(raw >> 16) & 0xFFu], c3 = lut[raw >> 24];
+        uint32_t o = __byte_perm(__byte_perm(c0, c1, 0x0040), __byte_perm(c2, c3, 0x0040), 0x5410);
+        // residues left in this word: keep that many low bytes, pad code in the others
+        const int left = len - (base + 4 * i);
+        const uint32_t keep = left >= 4 ? 0xFFFFFFFFu : left <= 0 ? 0u : (0xFFFFFFFFu >> (32 - 8 * left));
+        o = (o & keep) | ((BGCA_PAD_CODE * 0x01010101u) & ~keep);
+        bad |= o;
+        out[i] = o;
+    }
+    *reinterpret_cast<uint4 *>(dst + base) = make_uint4(out[0], out[1], out[2], out[3]);
+    return bad & 0x80808080u;
+}
+
 __global__ void __launch_bounds__(256)
-pack_kernel(const uint8_t *__restrict__ ascii, const int64_t *__restrict__ offsets_orig,
+pack_kernel(const uint8_t *__restrict__ ascii, const int64_t *__restrict__ src_off_sorted,
             const int32_t *__restrict__ order, const uint32_t *__restrict__ seq_off,
             const int32_t *__restrict__ seq_len, int32_t n, uint8_t *__restrict__ codes,
             unsigned long long *err_word)
 {
+    constexpr unsigned FULL = 0xFFFFFFFFu;
     __shared__ uint8_t lut[256];
     lut[threadIdx.x] = (uint8_t)encode_residue(threadIdx.x);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
-    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps_per_grid) {
-        const int orig = order[r];
-        const uint8_t *src = ascii + offsets_orig[orig];
-        const int len = seq_len[r];
-        const int padded = (len + 1 + 15) & ~15;
-        uint4 *dst = reinterpret_cast<uint4 *>(codes + seq_off[r]);
-        for (int base = lane * 16; base < padded; base += 32 * 16) {
-            uint32_t w[4] = {0, 0, 0, 0};
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+
+    // lanes 0..PACK_SEQS-1 hold the metadata of the block's sequences
+    auto fetch_meta = [&](int r0, long long &so, int &len, uint32_t &doff) {
+        const int r = r0 + lane;
+        const bool v = lane < PACK_SEQS && r < n;
+        so = v ? src_off_sorted[r] : 0;
+        len = v ? seq_len[r] : 0;
+        doff = v ? seq_off[r] : 0u;
+    };
+    long long so_n = 0;
+    int len_n = 0;
+    uint32_t doff_n = 0;
+    int r0 = gw * PACK_SEQS;
+    if (r0 < n) fetch_meta(r0, so_n, len_n, doff_n);
+    for (; r0 < n; r0 += warps_per_grid * PACK_SEQS) {
+        const long long so = so_n;
+        const int len = len_n;
+        const uint32_t doff = doff_n;
+        if (r0 + warps_per_grid * PACK_SEQS < n) fetch_meta(r0 + warps_per_grid * PACK_SEQS, so_n, len_n, doff_n);
+
+        // the block's chunks as one flat index space [0, total): sequence u owns [first[u], first[u+1]).
+        // The metadata stays in lanes 0..PACK_SEQS-1 and is fetched with lane-indexed shuffles.
+        int first[PACK_SEQS + 1];
+        first[0] = 0;
 #pragma unroll
-            for (int b = 0; b < 16; ++b) {
-                const int i = base + b;
-                uint32_t code = BGCA_PAD_CODE;
-                if (i < len) {
-                    code = lut[__ldg(src + i)];
-                    if (code == 255u) {
-                        atomicMin(err_word, ((unsigned long long)(uint32_t)orig << 32) |
-                                                (unsigned long long)(uint32_t)i);
-                        code = 22;  // 'X' keeps the batch well-formed; the call still fails
-                    }
-                }
-                w[b >> 2] |= code << (8 * (b & 3));
+        for (int u = 0; u < PACK_SEQS; ++u) {
+            const int Lu = __shfl_sync(FULL, len, u);     // 0 past the end of the batch
+            first[u + 1] = first[u] + (Lu > 0 ? (Lu + 16) >> 4 : 0);
+        }
+        const int total = first[PACK_SEQS];
+        auto locate = [&](int f, const uint8_t *&s_, uint8_t *&d_, int &l_, int &base_, int &u_) {
+            u_ = 0;
+            int f0 = 0;
+#pragma unroll
+            for (int u = 1; u < PACK_SEQS; ++u) {
+                const int in = (f >= first[u]);
+                u_ += in;
+                f0 += in * (first[u] - first[u - 1]);
             }
-            dst[base >> 4] = make_uint4(w[0], w[1], w[2], w[3]);
+            s_ = ascii + __shfl_sync(FULL, so, u_);
+            d_ = codes + __shfl_sync(FULL, doff, u_);
+            l_ = __shfl_sync(FULL, len, u_);
+            base_ = (f - f0) * 16;
+        };
+        for (int f_base = 0; f_base < total; f_base += 32 * PACK_ROUNDS) {
+            PackChunk ch[PACK_ROUNDS];
+            const uint8_t *s_[PACK_ROUNDS];
+            uint8_t *d_[PACK_ROUNDS];
+            int l_[PACK_ROUNDS], b_[PACK_ROUNDS], u_[PACK_ROUNDS];
+#pragma unroll
+            for (int k = 0; k < PACK_ROUNDS; ++k) {
+                const int f = f_base + 32 * k + lane;
+                locate(min(f, total - 1), s_[k], d_[k], l_[k], b_[k], u_[k]);
+                if (f >= total) l_[k] = -1;                       // no chunk for this lane in round k
+                ch[k] = pack_fetch(s_[k], l_[k], b_[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < PACK_ROUNDS; ++k) {
+                if (l_[k] < 0) continue;
+                if (pack_emit(ch[k], s_[k], l_[k], b_[k], d_[k], lut)) {
+                    // cold path: name the first illegal letter of this chunk, put 'X' in its place
+                    for (int i = 0; i < 16 && b_[k] + i < l_[k]; ++i)
+                        if (lut[s_[k][b_[k] + i]] == 255u) {
+                            atomicMin(err_word, ((unsigned long long)(uint32_t)order[r0 + u_[k]] << 32) |
+                                                    (unsigned long long)(uint32_t)(b_[k] + i));
+                            d_[k][b_[k] + i] = 22;
+                        }
+                }
+            }
         }
     }
 }
 
-cudaError_t launch_pack(const uint8_t *ascii, const int64_t *offsets_orig, const int32_t *order,
+cudaError_t launch_pack(const uint8_t *ascii, const int64_t *src_off_sorted, const int32_t *order,
                         const uint32_t *seq_off, const int32_t *seq_len, int32_t n, uint8_t *codes,
                         unsigned long long *err_word, cudaStream_t st)
 {
-    int grid = (n + 7) / 8;
-    if (grid > 148 * 8) grid = 148 * 8;
+    // persistent-ish grid: a multiple of the SM count, never more warps than sequence blocks
+    const int blocks_needed = (n + PACK_SEQS * 8 - 1) / (PACK_SEQS * 8);
+    int grid = 148 * 3;   // 78 registers -> 3 resident CTAs per SM; every warp loops over its blocks
+    if (grid > blocks_needed) grid = blocks_needed;
     if (grid < 1) grid = 1;
-    pack_kernel<<<grid, 256, 0, st>>>(ascii, offsets_orig, order, seq_off, seq_len, n, codes, err_word);
+    pack_kernel<<<grid, 256, 0, st>>>(ascii, src_off_sorted, order, seq_off, seq_len, n, codes, err_word);
     return cudaGetLastError();
 }
 

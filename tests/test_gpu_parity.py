@@ -122,6 +122,35 @@ def test_packer_matches_oracle_encoding():
         assert (seg[lens[o]:] == 24).all()
 
 
+def test_packer_alignment_long_sequences_and_device_input():
+    """K1's aligned-word loads: every source misalignment 0..15, lengths around the 16- and
+    512-byte boundaries, ASCII handed over as an unaligned device view."""
+    import torch
+    rng = np.random.default_rng(9)
+    lens = [1, 2, 15, 16, 17, 31, 32, 33, 255, 256, 257, 495, 496, 497, 511, 512, 513, 527, 528, 529, 1023, 1024,
+            1025, 2000, 3, 7, 11, 13, 5, 9]
+    seqs = [_rand(rng, n, "ARNDCQEGHILKMFPSTWYVBZX*") for n in lens]
+    eng = get_engine()
+    from bgclib_b200.engine import concat_ascii
+    ascii_, offsets = concat_ascii(seqs)
+    for shift in (0, 1, 5, 8, 15):
+        buf = torch.zeros(len(ascii_) + 64, dtype=torch.uint8, device="cuda")
+        view = buf[shift: shift + len(ascii_)]
+        view.copy_(torch.from_numpy(ascii_.copy()))
+        eng.pack_ascii(view, offsets)
+        codes, offs, order = eng.get_packed()
+        for r, o in enumerate(order):
+            seg = codes[offs[r]:offs[r + 1]]
+            assert len(seg) == (lens[o] + 16) // 16 * 16
+            assert (seg[: lens[o]] == oracle.encode(seqs[o])).all() and (seg[lens[o]:] == 24).all()
+    # the smallest (sequence, position) of an illegal letter is what the error names
+    bad = list(seqs)
+    bad[21] = bad[21][:700] + "U" + bad[21][701:900] + "J" + bad[21][901:]
+    bad[23] = bad[23][:1999] + "O"
+    with pytest.raises(ValueError, match="sequence 21 .* position 700"):
+        eng.pack(bad)
+
+
 def test_errors_mirror_biopython():
     with pytest.raises(ValueError, match="alphabet"):
         domain_pair_scores(["ACDEFG", "ACDUFG"])

@@ -70,44 +70,3 @@ def test_attach_adds_methods_without_state(ref):
     col = cls()
     pickle.dumps(col)
 
-
-def test_split_domain_merge_matches_reference_fix_core_split_domains():
-    """merged_domain_view against the REAL fix_core_split_domains (BGCtoolkit.py:575-687) run on
-    real BGCProtein/BGCDomain objects by tests/golden/make_split_golden.py."""
-    import json
-    from types import SimpleNamespace
-    from conftest import GOLDEN
-    from bgclib_b200.extract import merged_domain_view, split_domain_groups
-    cases = json.loads((GOLDEN / "split_domains.json").read_text())["cases"]
-    assert len(cases) == 400
-    merged = 0
-    for c in cases:
-        p = SimpleNamespace(identifier=c["identifier"], sequence="A" * 3000, domain_list=[])
-        p.domain_list = [SimpleNamespace(protein=p, ID=d[0], alias="", ali_from=d[1], ali_to=d[2], hmm_from=d[3],
-                                         hmm_to=d[4], score=d[5]) for d in c["domains"]]
-        before = list(p.domain_list)
-        view = merged_domain_view(p)
-        got = [[v.ID, v.ali_from, v.ali_to, v.hmm_from, v.hmm_to, v.score] for v in view]
-        assert got == c["after"], c["identifier"]
-        assert p.domain_list == before                                   # the protein is untouched
-        assert sum(v.n_fragments for v in view) == len(before)
-        merged += any(v.n_fragments > 1 for v in view)
-        for run in split_domain_groups(before):
-            assert len(run) >= 2 and len({before[k].ID for k in run}) == 1
-    assert merged > 100
-
-
-def test_extract_with_merged_split_domains():
-    from types import SimpleNamespace
-    from bgclib_b200 import extract
-    p = SimpleNamespace(identifier="P1", sequence="ACDEFGHIKLMNPQRSTVWY" * 5, domain_list=[], parent_cluster_id="B1",
-                        protein_type="PKS")
-    mk = lambda ID, a0, a1, h0, h1: SimpleNamespace(protein=p, ID=ID, alias="", ali_from=a0, ali_to=a1,  # noqa: E731
-                                                    hmm_from=h0, hmm_to=h1, score=1.0,
-                                                    get_sequence=lambda: p.sequence[a0:a1])
-    p.domain_list = [mk("KS", 0, 20, 1, 100), mk("KS", 25, 50, 120, 250), mk("AT", 60, 90, 1, 300)]
-    plain = extract([p])
-    fixed = extract([p], merge_split_domains=True)
-    assert [r.length for r in plain.records] == [20, 25, 30]
-    assert [(r.domain_id, r.ali_from, r.ali_to) for r in fixed.records] == [("KS", 0, 50), ("AT", 60, 90)]
-    assert fixed.sequences[0] == p.sequence[0:50]

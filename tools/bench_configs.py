@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--same-type", action="store_true", help="only same-type pairs (the BGC similarity plan)")
     ap.add_argument("--matrix", action="store_true", help="also materialise the n x n score matrix")
     ap.add_argument("--mode", default="local")
+    ap.add_argument("--stages-only", action="store_true",
+                    help="K1 and K5 alone (rowbest filled with random scores instead of running the DP kernels)")
     args = ap.parse_args()
 
     import torch
@@ -106,6 +108,30 @@ def main():
             dist.all_reduce(rowbest, op=dist.ReduceOp.MAX)
             dist.all_reduce(selfsc, op=dist.ReduceOp.MAX)
 
+    if args.stages_only:
+        rowbest.random_(0, 2000)
+        selfsc.random_(1, 3000)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > L2: evicts between repetitions
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        alg5 = 4 * n * B + 4 * n + 8 * B * B + 8 * B + (8 * B * B * 2 + 8 * B * B)
+        alg1 = int(col.ascii.nbytes) + packed_bytes
+        t1, t5 = [], []
+        for _ in range(6):
+            flush.fill_(1)
+            eng.pack_ascii(ascii_dev, col.offsets, types, col.bgc_of_seq, B)   # K1 (kernel time: ncu launch list)
+            flush.fill_(2)
+            e0.record()
+            eng.reduce_bgc(rowbest, selfsc)
+            e1.record()
+            torch.cuda.synchronize()
+            t5.append(e0.elapsed_time(e1))
+        ms5 = float(np.median(t5[1:]))
+        emit({"stage": "K5 bgc_sum + bgc_sim (cold L2, CUDA events)", "config": args.config, "n": n, "n_bgc": B,
+              "ms": ms5, "algorithmic_bytes": alg5, "gb_per_s": alg5 / (ms5 * 1e-3) / 1e9})
+        emit({"stage": "K1 pack_kernel", "config": args.config, "n": n, "algorithmic_bytes": alg1,
+              "note": "kernel duration: gpu__time_duration of pack_kernel in the ncu launch list of this command"})
+        emit({"stage": "done", "generate_s": gen_s})
+        return
     if args.mode == "local":
         fused()
         ms = sync_time(fused, args.steps)
