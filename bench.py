@@ -6,7 +6,8 @@
 
 A step = one pass of the hot path over the whole batch: every pair i<=j of the
 packed collection scored (local, BLOSUM62, -12/-1), results written to the
-n x n int32 matrix, and — for N>1 — combined with one NCCL all-reduce(max).
+n x n int32 matrix, and — for N>1 — combined with one NCCL reduce-scatter(max)
+that leaves rank r with its block of rows (the full matrix, sharded by rows).
 N=1 workload: BASELINE.json configs[2] (10k KS-like domains, ~420 aa).  N>1 is
 weak scaling: round(10000*sqrt(N)) domains from the same generator, so the cells
 per GPU stay constant.  metric = GCUPS = 1e9 DP cells/s over the UNIQUE pairs
@@ -182,13 +183,25 @@ def main():
     # inputs resident in HBM before the timed region: packed batch + this rank's tile list
     eng.pack_ascii(col.ascii, col.offsets)
     plan = eng.plan(same_type_only=False, rank=rank, world=world)
-    scores = torch.empty((n, n), dtype=torch.int32, device=dev)
+    from bgclib_b200.api import row_block
+    blk, r0, r1 = row_block(n, rank, world)
+    padded = torch.empty((blk * world, n), dtype=torch.int32, device=dev)   # rows >= n: reduce-scatter padding
+    scores = padded[:n]
+    mine = torch.empty((blk, n), dtype=torch.int32, device=dev) if world > 1 else None
 
     def step():
-        scores.fill_(INT32_MIN)           # n*n*4 B write (> L2 for the N=1 workload): also the L2 flush
+        padded.fill_(INT32_MIN)           # n*n*4 B write (> L2 for the N=1 workload): also the L2 flush
         eng.score(scores=scores)
-        if world > 1:
-            dist.all_reduce(scores, op=dist.ReduceOp.MAX)
+        if world > 1:                     # rank r keeps rows [r0, r1) of the combined matrix
+            dist.reduce_scatter_tensor(mine, padded, op=dist.ReduceOp.MAX)
+
+    if world > 1:                         # untimed: the row block equals the all-reduced matrix's rows
+        step()
+        full = scores.clone()
+        dist.all_reduce(full, op=dist.ReduceOp.MAX)
+        assert bool((full[r0:r1] == mine[: r1 - r0]).all()), "reduce-scatter block differs from all-reduce"
+        assert bool((full == full.T).all()) and bool((full.diagonal() > 0).all())
+        del full
 
     for _ in range(args.warmup):
         step()
@@ -222,7 +235,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         ascii_pin = torch.from_numpy(col.ascii.copy()).pin_memory()
-        out_pin = torch.empty((n, n), dtype=torch.int32).pin_memory() if rank == 0 else None
+        out_pin = torch.empty((n, n) if world == 1 else (blk, n), dtype=torch.int32).pin_memory()
         offsets = col.offsets
 
         def e2e_step():
@@ -231,11 +244,10 @@ def main():
             else:
                 eng.pack_ascii(ascii_pin.numpy(), offsets)                        # H2D inside
                 eng.plan(same_type_only=False, rank=rank, world=world)
-                scores.fill_(INT32_MIN)
+                padded.fill_(INT32_MIN)
                 eng.score(scores=scores)
-                dist.all_reduce(scores, op=dist.ReduceOp.MAX)
-                if rank == 0:
-                    out_pin.copy_(scores, non_blocking=False)                     # D2H inside
+                dist.reduce_scatter_tensor(mine, padded, op=dist.ReduceOp.MAX)
+                out_pin.copy_(mine, non_blocking=False)                           # D2H inside, every rank its rows
         e2e_step()
         torch.cuda.synchronize()
         if world > 1:
@@ -251,10 +263,11 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": total_cells / float(t.item()) / 1e9, "unit": "GCUPS (1e9 DP cells/s)",
-               "h2d_bytes_per_step": int(col.ascii.nbytes + col.offsets.nbytes + 20 * n),
-               "d2h_bytes_per_step": int(4 * n * n), "ms_per_step": 1e3 * float(t.item()),
+               "h2d_bytes_per_step": int(col.ascii.nbytes + col.offsets.nbytes + 20 * n) * world,
+               "d2h_bytes_per_step": int(4 * n * n) if world == 1 else int(4 * blk * world * n),
+               "ms_per_step": 1e3 * float(t.item()),
                "api": "bgca_score_all_host (C ABI, host pointers)" if world == 1 else
-                      "Engine.pack_ascii+plan+score + NCCL all-reduce + D2H on rank 0"}
+                      "Engine.pack_ascii+plan+score + NCCL reduce-scatter(max) + D2H of each rank's row block"}
         if rank == 0 and world == 1:
             m = out_pin.numpy()
             assert (np.diag(m) > 0).all() and (m[0] == m[:, 0]).all()

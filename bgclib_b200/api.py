@@ -56,6 +56,7 @@ class DomainPairScores:
     computed: Optional[np.ndarray]  # bool, same shape, when same_type_only masked some pairs, else None
     plan: dict                      # tile-plan statistics of this rank
     db_index: Optional[List[DomainRecord]] = None   # column identity of a query-vs-database run
+    rows: Optional[tuple] = None    # (r0, r1) when shard_rows kept only this rank's rows scores[r0:r1]
 
 
 @dataclass
@@ -69,6 +70,14 @@ class BGCSimilarity:
     db_bgc_ids: Optional[List[str]] = None          # column identity of a query-vs-database run
     db_self_score: Optional[np.ndarray] = None      # int64 [B_db]
     best_db: Optional[np.ndarray] = None            # int64 [B_db, B_query]: the database -> query direction
+
+
+def row_block(n: int, rank: int, world: int):
+    """Rows [r0, r1) of an n-row result that rank ``rank`` of ``world`` keeps under
+    ``shard_rows`` (equal blocks of ceil(n / world) rows; the last ranks may get fewer or none)."""
+    blk = -(-n // world)
+    r0 = min(n, rank * blk)
+    return blk, r0, min(n, r0 + blk)
 
 
 def _as_batch(source, unit, cbp_only, alias, domain_types) -> DomainBatch:
@@ -95,7 +104,7 @@ def _merge(q: DomainBatch, d: DomainBatch):
 def domain_pair_scores(source, *, database=None, mode="local", matrix="BLOSUM62", open_gap_score=-12,
                        extend_gap_score=-1, unit="domain", cbp_only=True, alias=None,
                        domain_types=None, same_type_only=False, device=None,
-                       return_device=False) -> DomainPairScores:
+                       return_device=False, shard_rows=False) -> DomainPairScores:
     """All-vs-all affine-gap alignment scores of the domain sequences in ``source``.
 
     Raises ValueError for an empty selection, a zero-length sequence or a letter
@@ -106,6 +115,12 @@ def domain_pair_scores(source, *, database=None, mode="local", matrix="BLOSUM62"
     ``database``: a second collection — only query x database pairs are scored ("a new set of
     BGCs against a precomputed database", BGClib/Readme.md:18) and ``scores`` is
     [n_query, n_database].
+
+    Under a ``torch.distributed`` process group every rank scores its share of the tile list.
+    By default one all-reduce(max) leaves the whole matrix on every rank; ``shard_rows=True``
+    uses a reduce-scatter(max) instead — half the NVLink traffic — and returns only this rank's
+    row block (``result.rows`` = (r0, r1), ``row_block``), so the device-to-host copies of the
+    ranks run in parallel.
     """
     batch = _as_batch(source, unit, cbp_only, alias, domain_types)
     n = len(batch)
@@ -123,14 +138,24 @@ def domain_pair_scores(source, *, database=None, mode="local", matrix="BLOSUM62"
         seqs, types, _ = _merge(batch, db)
         eng.pack(seqs, type_of_seq=types if same_type_only else None, n_query=n)
         plan = eng.plan(same_type_only=same_type_only, rank=rank, world=world, cross_only=True)
-        scores = torch.full((n, len(db)), INT32_MIN, dtype=torch.int32, device=eng.tdev)
+        ncols = len(db)
     else:
         eng.pack(batch.sequences, type_of_seq=batch.type_of_seq if same_type_only else None)
         plan = eng.plan(same_type_only=same_type_only, rank=rank, world=world)
-        scores = torch.full((n, n), INT32_MIN, dtype=torch.int32, device=eng.tdev)
-    eng.score(scores=scores)
-    if dist is not None:
-        dist.all_reduce(scores, op=dist.ReduceOp.MAX)
+        ncols = n
+    rows = (0, n) if shard_rows else None      # a single process holds every row
+    if dist is not None and shard_rows:
+        blk, r0, r1 = row_block(n, rank, world)
+        padded = torch.full((blk * world, ncols), INT32_MIN, dtype=torch.int32, device=eng.tdev)
+        eng.score(scores=padded[:n])
+        mine = torch.empty((blk, ncols), dtype=torch.int32, device=eng.tdev)
+        dist.reduce_scatter_tensor(mine, padded, op=dist.ReduceOp.MAX)
+        scores, rows = mine[: r1 - r0], (r0, r1)
+    else:
+        scores = torch.full((n, ncols), INT32_MIN, dtype=torch.int32, device=eng.tdev)
+        eng.score(scores=scores)
+        if dist is not None:
+            dist.all_reduce(scores, op=dist.ReduceOp.MAX)
     computed = None
     if same_type_only:
         computed = scores != INT32_MIN
@@ -138,9 +163,9 @@ def domain_pair_scores(source, *, database=None, mode="local", matrix="BLOSUM62"
             scores = torch.where(computed, scores, torch.zeros_like(scores))
     db_index = None if db is None else db.records
     if return_device:
-        return DomainPairScores(scores, batch.records, computed, plan, db_index)
+        return DomainPairScores(scores, batch.records, computed, plan, db_index, rows)
     return DomainPairScores(scores.cpu().numpy(), batch.records,
-                            None if computed is None else computed.cpu().numpy(), plan, db_index)
+                            None if computed is None else computed.cpu().numpy(), plan, db_index, rows)
 
 
 def bgc_similarity(source, *, database=None, matrix="BLOSUM62", open_gap_score=-12, extend_gap_score=-1,

@@ -125,8 +125,54 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
     // batches; large batches take longer tiles so the tile list (and the plan time) stays bounded
     const int spg = std::min(64, std::max(kSubjectsPerGroup, n / 1250));
 
+    // exact accounting of unique pairs (i<=j) per tile
+    auto tile_pairs = [&](const bgca_tile &T, int64_t &pairs, int64_t &cells) {
+        if (T.reserved) {                    // self-only tile of a cross plan
+            pairs = (T.qb >= 0) ? 2 : 1;
+            cells = (int64_t)len[T.qa] * len[T.qa] + (T.qb >= 0 ? (int64_t)len[T.qb] * len[T.qb] : 0);
+            return;
+        }
+        const int64_t sumL = pre[T.s_end] - pre[T.s_begin];
+        pairs = T.s_end - T.s_begin;
+        cells = (int64_t)len[T.qa] * sumL;
+        if (T.qb >= 0) {
+            int64_t p2 = T.s_end - T.s_begin, sl2 = sumL;
+            if (T.s_begin <= T.qa && T.qa < T.s_end) { p2 -= 1; sl2 -= len[T.qa]; }   // (qb, qa) mirrored
+            pairs += p2;
+            cells += (int64_t)len[T.qb] * sl2;
+        }
+    };
+
+    // Assignment over the exact cell counts: greedy "least-loaded rank takes the next tile".
+    // Small batches collect every tile and visit them heaviest-first (LPT: the order matters when
+    // a rank gets only a handful of tiles).  Large batches assign each tile as it is generated —
+    // list scheduling is within one tile of the mean whatever the order, and one tile is < 1e-4
+    // of a rank's load there — so no global tile list is built and nothing is sorted.
+    const bool small_plan = n < 4096;
+    std::vector<int64_t> load(world, 0);
+    auto consume = [&](const bgca_tile &T) {
+        int owner = 0;
+        for (int r = 1; r < world; ++r)
+            if (load[r] < load[owner]) owner = r;
+        load[owner] += T.cells;
+        int64_t pr, ce;
+        tile_pairs(T, pr, ce);
+        R.info.total_pairs += pr;
+        R.info.total_cells += ce;
+        if (owner != rank) return;
+        R.info.n_pairs += pr;
+        R.info.cells += ce;
+        R.info.cells_computed += T.cells;
+        if (T.variant == 0) R.info.n_fallback32++;
+        R.tiles.push_back(T);
+    };
     std::vector<bgca_tile> all;
-    all.reserve((size_t)n * ((size_t)n / (2 * 128 * (size_t)spg) + 2) / 2);
+    auto produce = [&](const bgca_tile &T) {
+        if (small_plan) all.push_back(T);
+        else consume(T);
+    };
+    if (!small_plan) R.tiles.reserve(((size_t)n * ((size_t)n / (2 * 128 * (size_t)spg) + 2) / 2) / (size_t)world + 64);
+
     int tb = 0;
     while (tb < n) {
         int te = n;
@@ -163,7 +209,7 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
                 T.variant = variant;
                 if (variant && !fits_int16(mode, max_abs_sub, open, extend, Lq, len[s1 - 1])) T.variant = 0;
                 T.cells = (int64_t)(La + Lb) * (pre[s1] - pre[s0]);
-                all.push_back(T);
+                produce(T);
             }
         }
         if (cross_only) {
@@ -180,7 +226,7 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
                     T.reserved = 1;
                     if (T.variant && !fits_int16(mode, max_abs_sub, open, extend, Lq, Lq)) T.variant = 0;
                     T.cells = (int64_t)(La + Lb) * (pre[T.s_end] - pre[T.s_begin]);
-                    all.push_back(T);
+                    produce(T);
                 }
                 r0 = r_end;
             }
@@ -188,56 +234,31 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
         tb = te;
     }
 
-    // exact accounting of unique pairs (i<=j) per tile
-    auto tile_pairs = [&](const bgca_tile &T, int64_t &pairs, int64_t &cells) {
-        if (T.reserved) {                    // self-only tile of a cross plan
-            pairs = (T.qb >= 0) ? 2 : 1;
-            cells = (int64_t)len[T.qa] * len[T.qa] + (T.qb >= 0 ? (int64_t)len[T.qb] * len[T.qb] : 0);
-            return;
-        }
-        const int64_t sumL = pre[T.s_end] - pre[T.s_begin];
-        pairs = T.s_end - T.s_begin;
-        cells = (int64_t)len[T.qa] * sumL;
-        if (T.qb >= 0) {
-            int64_t p2 = T.s_end - T.s_begin, sl2 = sumL;
-            if (T.s_begin <= T.qa && T.qa < T.s_end) { p2 -= 1; sl2 -= len[T.qa]; }   // (qb, qa) mirrored
-            pairs += p2;
-            cells += (int64_t)len[T.qb] * sl2;
-        }
-    };
-
-    // LPT assignment over the exact cell counts
-    std::vector<int> idx(all.size());
-    std::iota(idx.begin(), idx.end(), 0);
-    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return all[a].cells > all[b].cells; });
-    using Load = std::pair<int64_t, int>;
-    std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
-    for (int r = 0; r < world; ++r) heap.push({0, r});
-    std::vector<int> owner(all.size(), 0);
-    for (int i : idx) {
-        Load l = heap.top();
-        heap.pop();
-        owner[i] = l.second;
-        l.first += all[i].cells;
-        heap.push(l);
+    if (small_plan) {
+        std::vector<int> idx(all.size());
+        std::iota(idx.begin(), idx.end(), 0);
+        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return all[a].cells > all[b].cells; });
+        for (int i : idx) consume(all[i]);
+        // one contiguous run per kernel variant, larger variants first, heaviest tile first
+        std::stable_sort(R.tiles.begin(), R.tiles.end(), [](const bgca_tile &a, const bgca_tile &b) {
+            if (a.variant != b.variant) return a.variant > b.variant;
+            return a.cells > b.cells;
+        });
+    } else {
+        // one contiguous run per kernel variant (bgca_score launches run by run), larger variants
+        // first, generation order inside a run: a stable bucket pass over the few distinct variants
+        std::vector<int> keys;
+        for (const auto &T : R.tiles)
+            if (std::find(keys.begin(), keys.end(), T.variant) == keys.end()) keys.push_back(T.variant);
+        std::sort(keys.begin(), keys.end(), std::greater<int>());
+        std::vector<size_t> start(keys.size() + 1, 0);
+        auto bucket = [&](int v) { return (size_t)(std::find(keys.begin(), keys.end(), v) - keys.begin()); };
+        for (const auto &T : R.tiles) start[bucket(T.variant) + 1]++;
+        for (size_t k = 0; k < keys.size(); ++k) start[k + 1] += start[k];
+        std::vector<bgca_tile> grouped(R.tiles.size());
+        for (const auto &T : R.tiles) grouped[start[bucket(T.variant)]++] = T;
+        R.tiles.swap(grouped);
     }
-
-    for (size_t i = 0; i < all.size(); ++i) {
-        int64_t pr, ce;
-        tile_pairs(all[i], pr, ce);
-        R.info.total_pairs += pr;
-        R.info.total_cells += ce;
-        if (owner[i] != rank) continue;
-        R.info.n_pairs += pr;
-        R.info.cells += ce;
-        R.info.cells_computed += all[i].cells;
-        if (all[i].variant == 0) R.info.n_fallback32++;
-        R.tiles.push_back(all[i]);
-    }
-    std::stable_sort(R.tiles.begin(), R.tiles.end(), [](const bgca_tile &a, const bgca_tile &b) {
-        if (a.variant != b.variant) return a.variant > b.variant;
-        return a.cells > b.cells;
-    });
     R.info.n_tiles = (int64_t)R.tiles.size();
     int nv = 0, last = -1;
     for (const auto &T : R.tiles)

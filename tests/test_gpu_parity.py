@@ -434,3 +434,23 @@ def test_stats_rejects_sequences_beyond_32767():
     from bgclib_b200 import domain_pair_stats
     with pytest.raises(ValueError, match="32767"):
         domain_pair_stats(["A" * 40000, "ACD"], [[0, 1]])
+
+
+def test_shard_rows_under_a_process_group():
+    """The reduce-scatter path (row-sharded result) on a one-rank NCCL group."""
+    import socket
+    import torch.distributed as dist
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    rng = np.random.default_rng(12)
+    seqs = _related(rng, 3, 5, 40, 200)
+    want = oracle.all_pairs(seqs)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    try:
+        full = domain_pair_scores(seqs)
+        part = domain_pair_scores(seqs, shard_rows=True)
+    finally:
+        dist.destroy_process_group()
+    assert (full.scores == want).all() and full.rows is None
+    assert part.rows == (0, len(seqs)) and (part.scores == want).all()

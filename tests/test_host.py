@@ -328,3 +328,15 @@ def test_extract_with_merged_split_domains():
     assert [r.length for r in plain.records] == [20, 25, 30]
     assert [(r.domain_id, r.ali_from, r.ali_to) for r in fixed.records] == [("KS", 0, 50), ("AT", 60, 90)]
     assert fixed.sequences[0] == p.sequence[0:50]
+
+
+def test_row_block_covers_every_row_once():
+    from bgclib_b200.api import row_block
+    for n in (1, 7, 8, 9, 100, 28284):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                blk, r0, r1 = row_block(n, r, world)
+                assert 0 <= r0 <= r1 <= n and r1 - r0 <= blk and blk * world >= n
+                seen += list(range(r0, r1))
+            assert seen == list(range(n))
