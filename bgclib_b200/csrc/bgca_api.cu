@@ -122,8 +122,9 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
     for (int i = 0; i < n; ++i) pre[i + 1] = pre[i] + len[i];
 
     // subjects per alignment group and tile: 16 keeps >= 100 tiles per CTA slot on small
-    // batches; large batches take longer tiles so the tile list (and the plan time) stays bounded
-    const int spg = std::min(64, std::max(kSubjectsPerGroup, n / 1250));
+    // batches; larger batches take longer tiles (still > 150 per CTA slot at 10k sequences) so
+    // that the tile list, and with it the plan time inside every end-to-end call, stays small
+    const int spg = std::min(64, std::max(kSubjectsPerGroup, n / 300));
 
     // exact accounting of unique pairs (i<=j) per tile
     auto tile_pairs = [&](const bgca_tile &T, int64_t &pairs, int64_t &cells) {
@@ -316,6 +317,7 @@ struct bgca_engine {
     DevBuf<bgca_tile> d_tiles;
     DevBuf<int2> d_scratch;
     DevBuf<uint4> d_scratch_st;
+    DevBuf<int32_t> d_scores_host_call;   // bgca_score_all_host's n x n staging matrix
     // plan
     std::vector<bgca_tile> tiles;
     bgca_plan_info plan_info{};
@@ -373,7 +375,7 @@ int bgca_destroy(bgca_engine *e)
     e->d_ascii.release(); e->d_codes.release(); e->d_offsets_orig.release(); e->d_order.release();
     e->d_len.release(); e->d_type.release(); e->d_bgc.release(); e->d_bgc_start.release();
     e->d_bgc_doms.release(); e->d_counters.release(); e->d_pq.release(); e->d_ps.release();
-    e->d_seq_off.release(); e->d_err.release(); e->d_tiles.release(); e->d_scratch.release(); e->d_scratch_st.release();
+    e->d_seq_off.release(); e->d_err.release(); e->d_tiles.release(); e->d_scratch.release(); e->d_scratch_st.release(); e->d_scores_host_call.release();
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
@@ -815,15 +817,16 @@ int bgca_score_all_host(bgca_engine *e, const uint8_t *ascii, const int64_t *off
     if (rc != BGCA_OK) return rc;
     rc = bgca_plan(e, 0, 0, 0, 1, nullptr);
     if (rc != BGCA_OK) return rc;
-    int32_t *d_scores = nullptr;
+    // the device-side matrix is engine-owned scratch, kept across calls (repeated calls on
+    // same-sized batches pay no cudaMalloc/cudaFree)
     const size_t bytes = sizeof(int32_t) * (size_t)n * (size_t)n;
-    CUDA_TRY(cudaMalloc(&d_scores, bytes));
+    CUDA_TRY(e->d_scores_host_call.reserve((size_t)n * (size_t)n));
+    int32_t *d_scores = e->d_scores_host_call.p;
     cudaError_t err = cudaMemsetAsync(d_scores, 0, bytes, nullptr);
     if (err == cudaSuccess) {
         rc = bgca_score(e, d_scores, nullptr, nullptr, 0, nullptr);
         if (rc == BGCA_OK) err = cudaMemcpy(scores_host, d_scores, bytes, cudaMemcpyDeviceToHost);
     }
-    cudaFree(d_scores);
     if (rc != BGCA_OK) return rc;
     if (err != cudaSuccess) return fail(BGCA_ERR_CUDA, std::string("bgca_score_all_host: ") + cudaGetErrorString(err));
     return BGCA_OK;

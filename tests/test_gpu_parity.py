@@ -168,6 +168,28 @@ def test_errors_mirror_biopython():
     assert domain_pair_scores(["WW", "WW"]).scores.tolist() == [[22, 22], [22, 22]]
 
 
+@pytest.mark.parametrize("mode", ["local", "global"])
+@pytest.mark.parametrize("o,e", [(-10, -2), (-5, -5), (-1, 0), (0, 0), (-40, -3), (-12, -2)])
+def test_run_time_gap_scores_and_custom_matrices(mode, o, e):
+    """Gap scores outside the compiled presets (run-time operands) and substitution matrices
+    other than BLOSUM62: a random symmetric small-integer matrix and one large enough that the
+    planner must route every tile to the 32-bit kernel."""
+    rng = np.random.default_rng(abs(o) * 31 + abs(e) + (mode == "global"))
+    seqs = _related(rng, 3, 4, 30, 330, AA + "BZX*") + [_rand(rng, k, AA) for k in (1, 2, 17, 333)]
+    cm = oracle.MODE_LOCAL if mode == "local" else oracle.MODE_GLOBAL
+    res = domain_pair_scores(seqs, mode=mode, open_gap_score=o, extend_gap_score=e)
+    assert (res.scores == oracle.all_pairs(seqs, mode=cm, open_gap=o, extend_gap=e)).all()
+    m = rng.integers(-6, 9, (24, 24))
+    m = np.triu(m) + np.triu(m, 1).T
+    res = domain_pair_scores(seqs, mode=mode, matrix=m, open_gap_score=o, extend_gap_score=e)
+    assert (res.scores == oracle.all_pairs(seqs, mode=cm, sub=m.astype(np.int8), open_gap=o, extend_gap=e)).all()
+    assert res.plan["n_fallback32"] == 0
+    big = m * 14                                   # |s| up to 112: 112 * 333 leaves int16
+    res = domain_pair_scores(seqs, mode=mode, matrix=big, open_gap_score=o, extend_gap_score=e)
+    assert (res.scores == oracle.all_pairs(seqs, mode=cm, sub=big.astype(np.int8), open_gap=o, extend_gap=e)).all()
+    assert res.plan["n_fallback32"] > 0
+
+
 # ---- config 2: 37 Af293 BGCs -> BGC-pair similarity ----------------------------------------
 def _af293_collection(af293, ks_records, seed=20260102):
     """Config 2b: the 282-domain architecture of the 57 CBPs with the real
