@@ -98,7 +98,10 @@ def cpu_reference_run(col, seconds_target: float, nthreads: int = 0):
     """Times the oracle port (scalar int32 Gotoh, OpenMP over pairs) on a bounded
     prefix of the workload.  Returns (gcups, pairs_per_s, cores, sample description, seconds)."""
     import oracle
-    cores = oracle.num_threads() if nthreads <= 0 else nthreads
+    if nthreads <= 0:
+        # every host core, also under torchrun (which exports OMP_NUM_THREADS=1 to its workers)
+        nthreads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = nthreads
     probe = col.subset(24 * max(1, cores // 8 + 1))
     t0 = time.perf_counter()
     oracle.all_pairs(probe.sequences(), nthreads=nthreads)

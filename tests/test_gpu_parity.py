@@ -190,6 +190,59 @@ def test_run_time_gap_scores_and_custom_matrices(mode, o, e):
     assert res.plan["n_fallback32"] > 0
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_random_collections_stress(seed):
+    """Many small random collections: odd sequence counts (single query pairs, ragged subject
+    chunks), lengths straddling the G*K row boundaries of the kernel variants and the 16-byte
+    packing boundaries, families and unrelated sequences mixed, both modes, matrix and fused
+    BGC reduction — everything against the oracle."""
+    import torch
+    rng = np.random.default_rng(1000 + seed)
+    eng = get_engine()
+    for _ in range(10):
+        n = int(rng.integers(1, 70))
+        style = int(rng.integers(0, 4))
+        if style == 0:      # around a variant boundary G*K
+            g, k = int(rng.choice([8, 16, 32])), int(rng.integers(2, 33))
+            lens = np.clip(g * k + rng.integers(-3, 4, n), 1, 1024)
+        elif style == 1:    # wide spread
+            lens = rng.integers(1, 700, n)
+        elif style == 2:    # short domains (T/ACP-like)
+            lens = rng.integers(40, 100, n)
+        else:               # multiples of 16 +- 1
+            lens = np.clip(16 * rng.integers(1, 40, n) + rng.integers(-1, 2, n), 1, 1024)
+        anc = _rand(rng, 1100)
+        seqs = []
+        for L in lens:
+            if rng.random() < 0.6:
+                m = list(anc[: int(L)])
+                for _ in range(int(L * rng.uniform(0.0, 0.5))):
+                    m[int(rng.integers(0, L))] = AA[int(rng.integers(0, 20))]
+                seqs.append("".join(m))
+            else:
+                seqs.append(_rand(rng, L))
+        mode = "local" if rng.random() < 0.6 else "global"
+        cm = oracle.MODE_LOCAL if mode == "local" else oracle.MODE_GLOBAL
+        want = oracle.all_pairs(seqs, mode=cm)
+        got = domain_pair_scores(seqs, mode=mode).scores
+        assert (got == want).all(), (seed, n, style, mode)
+        if mode == "local":
+            B = int(rng.integers(1, 9))
+            T = int(rng.integers(1, 4))
+            bgc_of = rng.integers(0, B, n).astype(np.int32)
+            type_of = rng.integers(0, T, n).astype(np.int32)
+            eng.set_scoring()
+            eng.pack(seqs, type_of_seq=type_of, bgc_of_seq=bgc_of, n_bgc=B)
+            eng.plan(same_type_only=True)
+            rowbest = torch.zeros((n, B), dtype=torch.int32, device="cuda")
+            selfsc = torch.zeros(n, dtype=torch.int32, device="cuda")
+            eng.score(rowbest=rowbest, selfsc=selfsc)
+            sim, best, selfsum = eng.reduce_bgc(rowbest, selfsc)
+            o_sim, o_best, o_self, o_rowbest = oracle.bgc_similarity_np(want, bgc_of, type_of, B)
+            assert (rowbest.cpu().numpy() == o_rowbest).all() and (best.cpu().numpy() == o_best).all()
+            assert (selfsum.cpu().numpy() == o_self).all() and (sim.cpu().numpy() == o_sim).all()
+
+
 # ---- config 2: 37 Af293 BGCs -> BGC-pair similarity ----------------------------------------
 def _af293_collection(af293, ks_records, seed=20260102):
     """Config 2b: the 282-domain architecture of the 57 CBPs with the real
