@@ -63,6 +63,14 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr)
     return v;
 }
 
+// one token (byte) of the packed batch, zero-extended by the load itself
+__device__ __forceinline__ uint32_t ldg_token(const uint8_t *p)
+{
+    uint32_t v;
+    asm("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
 template <int G, int K>
 struct Pair16Cfg {
     static constexpr int CH = (K + 3) / 4;          // 16-byte chunks per lane per letter
@@ -179,6 +187,11 @@ gotoh_pair16_kernel(const ScoreParams p)
         uint32_t top_h = LOCAL ? open2 : pack2(2 * p.open);     // lane 0: Ho[-1][j]
         // column boundary (j = -1) of the row above this lane: Ho[i0-1][-1]
         const uint32_t hin0 = (LOCAL || t == 0) ? open2 : pack2(2 * p.open + (i0 - 1) * p.extend);
+        // local mode: the top boundary row is constant (Ho = open, F = 0), so lane 0 takes it with
+        // one LOP3 per value instead of a compare and two selects per step
+        uint32_t keep_in = (t == 0) ? 0u : 0xFFFFFFFFu;
+        uint32_t top_or = (t == 0) ? open2 : 0u;
+        asm volatile("" : "+r"(keep_in), "+r"(top_or));   // opaque: keeps ptxas from turning them back into selects
 
         // start of a subject whose first residue is c0: state for column 0
         auto begin_subject = [&](uint32_t c0) {
@@ -209,7 +222,8 @@ gotoh_pair16_kernel(const ScoreParams p)
 
         int ord = 0;                                            // subjects this lane has finished
         int wait = (n_g > 0) ? t : 0;                           // idle steps before this lane starts
-        const uint8_t *ptr = idle_ptr;                          // address of the token two steps ahead
+        const uint8_t *ptr = idle_ptr;                          // address of the last token fetched (pre-incremented:
+                                                                // the load then reads through the updated pointer, no copy)
         uint32_t inc = 0;
         uint32_t c = TOK_IDLE, c1 = TOK_IDLE;                   // token of this step / of the next step
 #pragma unroll
@@ -218,7 +232,7 @@ gotoh_pair16_kernel(const ScoreParams p)
             const uint8_t *s0 = p.codes + p.seq_off[s_first];
             c = __ldg(s0);
             c1 = __ldg(s0 + 1);
-            ptr = s0 + 2;
+            ptr = s0 + 1;
             inc = 1;
             begin_subject(c);
         }
@@ -226,11 +240,14 @@ gotoh_pair16_kernel(const ScoreParams p)
         for (int tau = 0; tau < nsteps; ++tau) {
             uint32_t h_in = __shfl_up_sync(FULL, h_out, 1, G);
             uint32_t f_in = __shfl_up_sync(FULL, f_out, 1, G);
-            uint32_t c2 = __ldg(ptr);
             ptr += inc;
-            if (t == 0) {                       // top boundary row: Ho[-1][j], F[-1][j]
+            uint32_t c2 = ldg_token(ptr);
+            if (LOCAL) {                        // top boundary row: Ho[-1][j] = open, F[-1][j] = 0
+                h_in = (h_in & keep_in) | top_or;
+                f_in &= keep_in;
+            } else if (t == 0) {                // global: Ho[-1][j] walks down the boundary
                 h_in = top_h;
-                f_in = LOCAL ? 0u : NEG16x2;
+                f_in = NEG16x2;
             }
             if (c < TOK_BOUNDARY) {
                 // ================= hot path: one residue of the current subject ========
@@ -295,7 +312,7 @@ gotoh_pair16_kernel(const ScoreParams p)
                     const uint8_t *sn = p.codes + p.seq_off[s_first + ord * NGROUPS];
                     c1 = __ldg(sn);
                     c2 = __ldg(sn + 1);
-                    ptr = sn + 2;
+                    ptr = sn + 1;
                     begin_subject(c1);
                 } else {
                     c1 = TOK_IDLE;
@@ -309,7 +326,7 @@ gotoh_pair16_kernel(const ScoreParams p)
                     const uint8_t *s0 = p.codes + p.seq_off[s_first];
                     c1 = __ldg(s0);
                     c2 = __ldg(s0 + 1);
-                    ptr = s0 + 2;
+                    ptr = s0 + 1;
                     inc = 1;
                     begin_subject(c1);
                 }
