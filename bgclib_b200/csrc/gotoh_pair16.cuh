@@ -222,9 +222,10 @@ gotoh_pair16_kernel(const ScoreParams p)
 
         int ord = 0;                                            // subjects this lane has finished
         int wait = (n_g > 0) ? t : 0;                           // idle steps before this lane starts
-        const uint8_t *ptr = idle_ptr;                          // address of the last token fetched (pre-incremented:
-                                                                // the load then reads through the updated pointer, no copy)
-        uint32_t inc = 0;
+        // offset of the last token fetched.  Every step advances it by one and loads through the
+        // updated offset; a lane on idle tokens is put back on the header of idle bytes in the
+        // cold path, so the hot loop carries no per-lane increment
+        uint32_t off = 0;                                       // byte offset into p.codes (0 = idle header)
         uint32_t c = TOK_IDLE, c1 = TOK_IDLE;                   // token of this step / of the next step
 #pragma unroll
         for (int k = 0; k < K; ++k) { Tn[k] = 0; E[k] = 0; }
@@ -232,16 +233,15 @@ gotoh_pair16_kernel(const ScoreParams p)
             const uint8_t *s0 = p.codes + p.seq_off[s_first];
             c = __ldg(s0);
             c1 = __ldg(s0 + 1);
-            ptr = s0 + 1;
-            inc = 1;
+            off = p.seq_off[s_first] + 1;
             begin_subject(c);
         }
 
         for (int tau = 0; tau < nsteps; ++tau) {
             uint32_t h_in = __shfl_up_sync(FULL, h_out, 1, G);
             uint32_t f_in = __shfl_up_sync(FULL, f_out, 1, G);
-            ptr += inc;
-            uint32_t c2 = ldg_token(ptr);
+            off += 1;
+            uint32_t c2 = ldg_token(p.codes + off);
             if (LOCAL) {                        // top boundary row: Ho[-1][j] = open, F[-1][j] = 0
                 h_in = (h_in & keep_in) | top_or;
                 f_in &= keep_in;
@@ -312,22 +312,21 @@ gotoh_pair16_kernel(const ScoreParams p)
                     const uint8_t *sn = p.codes + p.seq_off[s_first + ord * NGROUPS];
                     c1 = __ldg(sn);
                     c2 = __ldg(sn + 1);
-                    ptr = sn + 1;
+                    off = p.seq_off[s_first + ord * NGROUPS] + 1;
                     begin_subject(c1);
                 } else {
                     c1 = TOK_IDLE;
                     c2 = TOK_IDLE;
-                    ptr = idle_ptr;
-                    inc = 0;
+                    off = 0;
                 }
-            } else if (wait > 0) {
-                // ================= cold path: wind-up of lane t (t idle steps) ===========
-                if (--wait == 0) {
+            } else {
+                // ================= cold path: idle token (wind-up of lane t, or stream finished) ====
+                off = 0;                        // stay on the header of idle bytes
+                if (wait > 0 && --wait == 0) {
                     const uint8_t *s0 = p.codes + p.seq_off[s_first];
                     c1 = __ldg(s0);
                     c2 = __ldg(s0 + 1);
-                    ptr = s0 + 1;
-                    inc = 1;
+                    off = p.seq_off[s_first] + 1;
                     begin_subject(c1);
                 }
             }
