@@ -63,9 +63,8 @@ int pick_variant(int Lq, int mode)
     int best = 0;
     double best_cost = 0.0;
     const int force_g = forced_group_width();
-    // global-mode kernels carry a second (final-column) copy of the column pass and spill
-    // beyond K = 19 at two CTAs per SM: stay below that whenever a wider group covers Lq
-    const int k_cap = (mode == BGCA_MODE_GLOBAL && Lq <= 32 * 19) ? 19 : 32;
+    (void)mode;   // local and global kernels have the same register budget
+    const int k_cap = 32;
     for (int v = 0; v < kNumVariants; ++v) {
         const int G = kVariants[v].G, K = kVariants[v].K;
         if (G * K < Lq || K > k_cap) continue;

@@ -41,8 +41,6 @@
 //   best = max3(best, H_even, H_odd)     VIMNMX3.S16x2          alu pipe, every 2nd cell (local)
 // = 5.5 issue slots per 2 cells of which 3.5 on the alu pipe (local); 5 / 3 (global).
 #pragma once
-#include <type_traits>
-
 #include "common.cuh"
 
 namespace bgca {
@@ -80,10 +78,9 @@ struct Pair16Cfg {
     static constexpr int PROF_BYTES = PROF_ROWS * ROW_BYTES;
     static constexpr int BEST_BYTES = NGROUPS * 32 * 2 * 4;   // per group: ring of 32 (lo, hi) slots
     static constexpr int SMEM_BYTES = PROF_BYTES + BEST_BYTES + 2 * LPAD + NSYM * NSYM + 16;
-    // registers: 2K state + 4CH profile + ~24 -> pick CTAs/SM so ptxas has room.  Global mode
-    // carries a second (final-column) copy of the column pass and needs a few more.
-    static constexpr int MIN_CTAS_LOCAL = (K <= 8) ? 5 : (K <= 14) ? 4 : (K <= 18) ? 3 : 2;
-    static constexpr int MIN_CTAS_GLOBAL = (K <= 8) ? 4 : (K <= 16) ? 3 : 2;
+    // registers: 2K state + 4CH profile + ~24 -> pick CTAs/SM so ptxas has room.
+    static constexpr int MIN_CTAS_LOCAL = (K <= 6) ? 5 : (K <= 14) ? 4 : (K <= 18) ? 3 : 2;
+    static constexpr int MIN_CTAS_GLOBAL = (K <= 4) ? 5 : (K <= 9) ? 4 : (K <= 14) ? 3 : 2;   // a few more live values (boundary walk)
 };
 
 // Gap presets: with the gap scores known at compile time the DPX ops take them as
@@ -181,7 +178,6 @@ gotoh_pair16_kernel(const ScoreParams p)
         // Tn[k] = Ho[i0+k-1][j-1] + (sub(q_{i0+k}, residue j) - open)   diagonal term of the NEXT cell
         // E[k]  = E[i0+k][j]                                            already advanced to column j
         uint32_t Tn[K], E[K];
-        uint32_t capA = 0, capB = 0;    // global mode: Ho[La-1][last column] / Ho[Lb-1][last column]
         uint32_t best = 0;
         uint32_t h_out = 0, f_out = 0;
         uint32_t top_h = LOCAL ? open2 : pack2(2 * p.open);     // lane 0: Ho[-1][j]
@@ -251,10 +247,7 @@ gotoh_pair16_kernel(const ScoreParams p)
             }
             if (c < TOK_BOUNDARY) {
                 // ================= hot path: one residue of the current subject ========
-                // LAST (global mode only): this is the subject's final column — the lanes that
-                // own rows La-1 / Lb-1 keep their Ho for the boundary step.
-                auto column = [&](auto last_tag) {
-                    constexpr bool LAST = decltype(last_tag)::value;
+                {
                     const uint32_t a = prof_lane + c1 * (uint32_t)Cfg::ROW_BYTES;   // row of the NEXT token
                     uint32_t P[CH * 4];
 #pragma unroll
@@ -271,10 +264,6 @@ gotoh_pair16_kernel(const ScoreParams p)
                         Tn[k] = __vadd2(up, P[k]);              // diagonal term of (k, j+1)
                         up = __vadd2(h, open2);                 // Ho[k][j]
                         E[k] = __viaddmax_s16x2(E[k], ext2, up);   // E[k][j+1]
-                        if (LAST) {
-                            if (i0 + k == La - 1) capA = up;
-                            if (i0 + k == Lb - 1) capB = up;
-                        }
                         if (LOCAL) {
                             if (k & 1) best = __vimax3_s16x2(best, h_prev, h);
                             else if (k == K - 1) best = __vmaxs2(best, h);
@@ -284,9 +273,7 @@ gotoh_pair16_kernel(const ScoreParams p)
                     h_out = up;
                     f_out = F;
                     if (!LOCAL) top_h = __vadd2(top_h, ext2);
-                };
-                if (!LOCAL && c1 == TOK_BOUNDARY) column(std::true_type{});
-                else column(std::false_type{});
+                }
             } else if (c == TOK_BOUNDARY) {
                 // ================= cold path: the subject just ended ====================
                 const int s = s_first + ord * NGROUPS;
@@ -303,9 +290,24 @@ gotoh_pair16_kernel(const ScoreParams p)
                         emit_pair(p, qb, s, b);
                     }
                 } else {
-                    // captured by the final-column pass of the lanes that own those rows
-                    if (i0 <= La - 1 && La - 1 < i0 + K) emit_pair(p, qa, s, (int)(int16_t)(capA & 0xFFFFu) - p.open);
-                    if (i0 <= Lb - 1 && Lb - 1 < i0 + K) emit_pair(p, qb, s, (int)(int16_t)(capB >> 16) - p.open);
+                    // H[row][last column] is still in the lane's state: the last column pass built
+                    // Tn[r+1] = Ho[r] + (profile row of the boundary token = 0 - open) = H[r], and the
+                    // bottom row of the lane left h_out = Ho[K-1].  Picked out here, on the cold path,
+                    // so the hot loop carries no capture code.
+                    auto final_h = [&](int r) {
+                        uint32_t v = __vsub2(h_out, open2);
+                        // one predicated select per row, as opaque asm: written as a plain
+                        // "if (r + 1 == k) v = Tn[k]" chain, ptxas turns Tn[] into an indexed local
+                        // array and stores it to the stack in every hot step
+#pragma unroll
+                        for (int k = 1; k < K; ++k)
+                            asm("{\n\t.reg .pred q;\n\tsetp.eq.s32 q, %1, %2;\n\tselp.b32 %0, %3, %0, q;\n\t}"
+                                : "+r"(v) : "r"(r + 1), "r"(k), "r"(Tn[k]));
+                        return v;
+                    };
+                    const int ra = La - 1 - i0, rb = Lb - 1 - i0;
+                    if (ra >= 0 && ra < K) emit_pair(p, qa, s, (int)(int16_t)(final_h(ra) & 0xFFFFu));
+                    if (rb >= 0 && rb < K) emit_pair(p, qb, s, (int)(int16_t)(final_h(rb) >> 16));
                 }
                 ++ord;
                 if (ord < n_g) {
