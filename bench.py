@@ -275,6 +275,45 @@ def main():
             m = out_pin.numpy()
             assert (np.diag(m) > 0).all() and (m[0] == m[:, 0]).all()
 
+    # ---- the HBM-bound stages, measured live (rank 0, N=1 only; not part of the timed step) -------
+    stages = None
+    if rank == 0 and world == 1:
+        try:
+            hbm_peak = float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"])
+            peak_src = "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            hbm_peak, peak_src = 6462.0, "fallback: copy bandwidth measured on this pool's B200s (B200_PROFILING.md)"
+        from bgclib_b200 import synth as _synth
+        big = _synth.nrps_pks_100k(4167)                       # BASELINE config 5: ~1e5 domains, 4167 BGCs
+        nb, Bb = len(big), big.n_bgc
+        ascii_dev = torch.from_numpy(big.ascii.copy()).to(dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        k1, k5 = [], []
+        rowbest = torch.randint(0, 2000, (nb, Bb), dtype=torch.int32, device=dev)
+        selfsc = torch.randint(1, 3000, (nb,), dtype=torch.int32, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(6):
+            flush.fill_(1)                                     # evict L2 (126 MB) between repetitions
+            eng.pack_ascii(ascii_dev, big.offsets, big.type_of_seq, big.bgc_of_seq, Bb)
+            k1.append(eng.last_pack_ms())
+            flush.fill_(2)
+            e0.record()
+            eng.reduce_bgc(rowbest, selfsc)
+            e1.record()
+            torch.cuda.synchronize()
+            k5.append(e0.elapsed_time(e1))
+        k1_ms, k5_ms = statistics.median(k1[1:]), statistics.median(k5[1:])
+        k1_bytes = int(big.ascii.nbytes) + int(eng._lib.bgca_packed_bytes(eng._h))
+        k5_bytes = 4 * nb * Bb + 4 * nb + 8 * Bb * Bb + 8 * Bb + 3 * 8 * Bb * Bb
+        stages = {"workload": f"{nb} synthetic NRPS/PKS domains in {Bb} BGCs (BASELINE config 5), cold L2",
+                  "peak_gbs": hbm_peak, "peak_source": peak_src,
+                  "k1_pack": {"ms": k1_ms, "algorithmic_bytes": k1_bytes, "gbs": k1_bytes / k1_ms / 1e6,
+                              "frac": k1_bytes / k1_ms / 1e6 / hbm_peak},
+                  "k5_bgc_reduce": {"ms": k5_ms, "algorithmic_bytes": k5_bytes, "gbs": k5_bytes / k5_ms / 1e6,
+                                    "frac": k5_bytes / k5_ms / 1e6 / hbm_peak}}
+        del rowbest, selfsc, flush, ascii_dev
+        eng.pack_ascii(col.ascii, col.offsets)                 # leave the engine on the bench workload
+
     if rank == 0:
         sm_mhz = clocks.get("sm_mhz") or 1965.0
         peaks = {}
@@ -330,7 +369,7 @@ def main():
                        "tiles_rank0": plan["n_tiles"], "kernel_variants_rank0": plan["n_variants"]},
             "pairs_per_s": total_pairs / (ms_per_step * 1e-3),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "hbm_stages": stages,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -325,6 +325,8 @@ struct bgca_engine {
     int last_launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
+    cudaEvent_t evp0 = nullptr, evp1 = nullptr;   // around the K1 kernel of the last bgca_pack
+    bool pack_timed = false;
     // side streams: the per-variant DP kernels are persistent, so launching them on
     // different streams lets the tail of one overlap the head of the next
     static constexpr int kSideStreams = 4;
@@ -358,6 +360,8 @@ int bgca_create(int device, bgca_engine **out)
     E->n_sm = prop.multiProcessorCount;
     CUDA_TRY(cudaEventCreate(&E->ev0));
     CUDA_TRY(cudaEventCreate(&E->ev1));
+    CUDA_TRY(cudaEventCreate(&E->evp0));
+    CUDA_TRY(cudaEventCreate(&E->evp1));
     CUDA_TRY(cudaEventCreateWithFlags(&E->ev_fork, cudaEventDisableTiming));
     for (int i = 0; i < bgca_engine::kSideStreams; ++i) {
         CUDA_TRY(cudaStreamCreateWithFlags(&E->side[i], cudaStreamNonBlocking));
@@ -377,6 +381,8 @@ int bgca_destroy(bgca_engine *e)
     e->d_seq_off.release(); e->d_err.release(); e->d_tiles.release(); e->d_scratch.release(); e->d_scratch_st.release(); e->d_scores_host_call.release();
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->evp0) cudaEventDestroy(e->evp0);
+    if (e->evp1) cudaEventDestroy(e->evp1);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     for (int i = 0; i < bgca_engine::kSideStreams; ++i) {
         if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
@@ -513,8 +519,11 @@ int bgca_pack(bgca_engine *e, const uint8_t *ascii, const int64_t *offsets, int3
     CUDA_TRY(cudaMemsetAsync(e->d_err.p, 0xFF, sizeof(unsigned long long), st));
     CUDA_TRY(cudaMemsetAsync(e->d_codes.p, 25, kPackedHeader, st));
     CUDA_TRY(cudaMemsetAsync(e->d_codes.p + off, BGCA_PAD_CODE, 16, st));
+    CUDA_TRY(cudaEventRecord(e->evp0, st));
     CUDA_TRY(launch_pack(d_src, e->d_offsets_orig.p, e->d_order.p, e->d_seq_off.p, e->d_len.p, n,
                          e->d_codes.p, e->d_err.p, st));
+    CUDA_TRY(cudaEventRecord(e->evp1, st));
+    e->pack_timed = true;
     unsigned long long err = 0;
     CUDA_TRY(cudaMemcpyAsync(&err, e->d_err.p, sizeof(err), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -839,6 +848,15 @@ int bgca_last_dp_ms(bgca_engine *e, float *ms)
     CUDA_TRY(cudaSetDevice(e->device));
     CUDA_TRY(cudaEventSynchronize(e->ev1));
     CUDA_TRY(cudaEventElapsedTime(ms, e->ev0, e->ev1));
+    return BGCA_OK;
+}
+
+int bgca_last_pack_ms(bgca_engine *e, float *ms)
+{
+    if (!e || !ms || !e->pack_timed) return fail(BGCA_ERR_INVALID, "bgca_last_pack_ms: no bgca_pack yet");
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaEventSynchronize(e->evp1));
+    CUDA_TRY(cudaEventElapsedTime(ms, e->evp0, e->evp1));
     return BGCA_OK;
 }
 

@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = (
     "bgca_version", "bgca_last_error", "bgca_create", "bgca_destroy", "bgca_set_scoring",
     "bgca_pack", "bgca_packed_bytes", "bgca_get_packed", "bgca_plan", "bgca_plan_host",
     "bgca_score", "bgca_score_pairs32", "bgca_pair_stats", "bgca_reduce_bgc", "bgca_score_all_host",
-    "bgca_last_launches", "bgca_last_dp_ms", "bgca_dpx_probe",
+    "bgca_last_launches", "bgca_last_dp_ms", "bgca_last_pack_ms", "bgca_dpx_probe",
 )
 
 
@@ -85,6 +85,7 @@ def load_library():
     lib.bgca_score_all_host.argtypes = [vp, vp, vp, i32, vp]
     lib.bgca_last_launches.argtypes = [vp]
     lib.bgca_last_dp_ms.argtypes = [vp, P(ctypes.c_float)]
+    lib.bgca_last_pack_ms.argtypes = [vp, P(ctypes.c_float)]
     lib.bgca_dpx_probe.argtypes = [ctypes.c_int, P(ctypes.c_double), i32]
     for name in EXPORTED_SYMBOLS:
         getattr(lib, name)   # AttributeError here = header and library out of step
@@ -323,6 +324,11 @@ class Engine:
 
     def last_launches(self) -> int:
         return int(self._lib.bgca_last_launches(self._h))
+
+    def last_pack_ms(self) -> float:
+        ms = ctypes.c_float(0)
+        _check(self._lib.bgca_last_pack_ms(self._h, ctypes.byref(ms)))
+        return float(ms.value)
 
     def last_dp_ms(self) -> float:
         ms = ctypes.c_float(0)

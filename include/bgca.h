@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define BGCA_VERSION 102
+#define BGCA_VERSION 103
 
 #define BGCA_MODE_LOCAL 0  /* Smith-Waterman/Gotoh, result = best cell, >= 0        */
 #define BGCA_MODE_GLOBAL 1 /* Needleman-Wunsch/Gotoh, end gaps cost like internal   */
@@ -178,6 +178,8 @@ int bgca_score_all_host(bgca_engine *e, const uint8_t *ascii, const int64_t *off
  * stream is synchronised). */
 int bgca_last_launches(const bgca_engine *e);
 int bgca_last_dp_ms(bgca_engine *e, float *ms);
+/* Device time of the K1 kernel of the last bgca_pack() in ms (CUDA events on its stream). */
+int bgca_last_pack_ms(bgca_engine *e, float *ms);
 
 /* Calibration microbenchmark: issue rate of the DPX/ALU ops
  * the DP kernels are made of.  Fills out[0..n) with lane-ops per clock per SM
