@@ -49,25 +49,28 @@ struct PackChunk {
     uint32_t w[5];
 };
 
-__device__ __forceinline__ PackChunk pack_fetch(const uint8_t *src, int len, int base)
+// abase = the ASCII buffer aligned down to 4 bytes, mis = its misalignment; so = byte offset of
+// the sequence in the buffer.  All index math is 32-bit (a batch is < 4 GiB); the word index is
+// clamped to the word that holds the sequence's last residue, so every load is in bounds and
+// there is no branch around it.
+__device__ __forceinline__ PackChunk pack_fetch(const uint32_t *__restrict__ abase, uint32_t mis, uint32_t so,
+                                                int len, int base)
 {
     PackChunk c;
-    const uintptr_t p = reinterpret_cast<uintptr_t>(src) + (uintptr_t)base;
-    const uintptr_t end = reinterpret_cast<uintptr_t>(src) + (uintptr_t)len;
-    const uint32_t *a = reinterpret_cast<const uint32_t *>(p & ~(uintptr_t)3);
+    const uint32_t w = (so + mis + (uint32_t)base) >> 2;
+    const uint32_t last = (so + mis + (uint32_t)len - 1u) >> 2;
 #pragma unroll
-    for (int i = 0; i < 5; ++i)
-        c.w[i] = (base < len && reinterpret_cast<uintptr_t>(a + i) < end) ? __ldg(a + i) : 0u;
+    for (int i = 0; i < 5; ++i) c.w[i] = __ldg(abase + min(w + (uint32_t)i, last));
     return c;
 }
 
 // realign (one funnel shift per word), encode through the shared table, blank what lies past
 // the sequence with the pad code, one 128-bit store.  Returns the OR of the encoded words: a
 // set bit 7 in any byte = an illegal letter somewhere in this chunk.
-__device__ __forceinline__ uint32_t pack_emit(const PackChunk &c, const uint8_t *src, int len, int base,
+__device__ __forceinline__ uint32_t pack_emit(const PackChunk &c, uint32_t mis, uint32_t so, int len, int base,
                                               uint8_t *dst, const uint8_t *lut)
 {
-    const uint32_t bits = (uint32_t)((reinterpret_cast<uintptr_t>(src) + (uintptr_t)base) & 3) * 8;
+    const uint32_t bits = ((so + mis + (uint32_t)base) & 3u) * 8u;
     uint32_t out[4], bad = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -75,9 +78,9 @@ __device__ __forceinline__ uint32_t pack_emit(const PackChunk &c, const uint8_t 
         const uint32_t c0 = lut[raw & 0xFFu], c1 = lut[(raw >> 8) & 0xFFu];
         const uint32_t c2 = lut[(raw >> 16) & 0xFFu], c3 = lut[raw >> 24];
         uint32_t o = __byte_perm(__byte_perm(c0, c1, 0x0040), __byte_perm(c2, c3, 0x0040), 0x5410);
-        // residues left in this word: keep that many low bytes, pad code in the others
-        const int left = len - (base + 4 * i);
-        const uint32_t keep = left >= 4 ? 0xFFFFFFFFu : left <= 0 ? 0u : (0xFFFFFFFFu >> (32 - 8 * left));
+        // residues left in this word (0..4): keep that many low bytes, pad code in the others
+        const int nb = min(max(len - (base + 4 * i), 0), 4);
+        const uint32_t keep = __funnelshift_lc(0xFFFFFFFFu, 0u, 8 * nb);
         o = (o & keep) | ((BGCA_PAD_CODE * 0x01010101u) & ~keep);
         bad |= o;
         out[i] = o;
@@ -99,22 +102,24 @@ pack_kernel(const uint8_t *__restrict__ ascii, const int64_t *__restrict__ src_o
     const int lane = threadIdx.x & 31;
     const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(ascii) & 3);
+    const uint32_t *abase = reinterpret_cast<const uint32_t *>(ascii - mis);
 
     // lanes 0..PACK_SEQS-1 hold the metadata of the block's sequences
-    auto fetch_meta = [&](int r0, long long &so, int &len, uint32_t &doff) {
+    auto fetch_meta = [&](int r0, uint32_t &so, int &len, uint32_t &doff) {
         const int r = r0 + lane;
         const bool v = lane < PACK_SEQS && r < n;
-        so = v ? src_off_sorted[r] : 0;
+        so = v ? (uint32_t)src_off_sorted[r] : 0u;
         len = v ? seq_len[r] : 0;
         doff = v ? seq_off[r] : 0u;
     };
-    long long so_n = 0;
+    uint32_t so_n = 0;
     int len_n = 0;
     uint32_t doff_n = 0;
     int r0 = gw * PACK_SEQS;
     if (r0 < n) fetch_meta(r0, so_n, len_n, doff_n);
     for (; r0 < n; r0 += warps_per_grid * PACK_SEQS) {
-        const long long so = so_n;
+        const uint32_t so = so_n;
         const int len = len_n;
         const uint32_t doff = doff_n;
         if (r0 + warps_per_grid * PACK_SEQS < n) fetch_meta(r0 + warps_per_grid * PACK_SEQS, so_n, len_n, doff_n);
@@ -129,7 +134,7 @@ pack_kernel(const uint8_t *__restrict__ ascii, const int64_t *__restrict__ src_o
             first[u + 1] = first[u] + (Lu > 0 ? (Lu + 16) >> 4 : 0);
         }
         const int total = first[PACK_SEQS];
-        auto locate = [&](int f, const uint8_t *&s_, uint8_t *&d_, int &l_, int &base_, int &u_) {
+        auto locate = [&](int f, uint32_t &s_, uint8_t *&d_, int &l_, int &base_, int &u_) {
             u_ = 0;
             int f0 = 0;
 #pragma unroll
@@ -138,30 +143,32 @@ pack_kernel(const uint8_t *__restrict__ ascii, const int64_t *__restrict__ src_o
                 u_ += in;
                 f0 += in * (first[u] - first[u - 1]);
             }
-            s_ = ascii + __shfl_sync(FULL, so, u_);
+            s_ = __shfl_sync(FULL, so, u_);
             d_ = codes + __shfl_sync(FULL, doff, u_);
             l_ = __shfl_sync(FULL, len, u_);
             base_ = (f - f0) * 16;
         };
         for (int f_base = 0; f_base < total; f_base += 32 * PACK_ROUNDS) {
             PackChunk ch[PACK_ROUNDS];
-            const uint8_t *s_[PACK_ROUNDS];
+            uint32_t s_[PACK_ROUNDS];
             uint8_t *d_[PACK_ROUNDS];
             int l_[PACK_ROUNDS], b_[PACK_ROUNDS], u_[PACK_ROUNDS];
+            bool have[PACK_ROUNDS];
 #pragma unroll
             for (int k = 0; k < PACK_ROUNDS; ++k) {
                 const int f = f_base + 32 * k + lane;
-                locate(min(f, total - 1), s_[k], d_[k], l_[k], b_[k], u_[k]);
-                if (f >= total) l_[k] = -1;                       // no chunk for this lane in round k
-                ch[k] = pack_fetch(s_[k], l_[k], b_[k]);
+                have[k] = f < total;                              // a lane without a chunk in round k
+                locate(min(f, total - 1), s_[k], d_[k], l_[k], b_[k], u_[k]);   // re-reads the last one
+                ch[k] = pack_fetch(abase, mis, s_[k], l_[k], b_[k]);
             }
 #pragma unroll
             for (int k = 0; k < PACK_ROUNDS; ++k) {
-                if (l_[k] < 0) continue;
-                if (pack_emit(ch[k], s_[k], l_[k], b_[k], d_[k], lut)) {
+                if (!have[k]) continue;
+                if (pack_emit(ch[k], mis, s_[k], l_[k], b_[k], d_[k], lut)) {
                     // cold path: name the first illegal letter of this chunk, put 'X' in its place
+#pragma unroll 1
                     for (int i = 0; i < 16 && b_[k] + i < l_[k]; ++i)
-                        if (lut[s_[k][b_[k] + i]] == 255u) {
+                        if (lut[ascii[s_[k] + b_[k] + i]] == 255u) {
                             atomicMin(err_word, ((unsigned long long)(uint32_t)order[r0 + u_[k]] << 32) |
                                                     (unsigned long long)(uint32_t)(b_[k] + i));
                             d_[k][b_[k] + i] = 22;
@@ -178,7 +185,7 @@ cudaError_t launch_pack(const uint8_t *ascii, const int64_t *src_off_sorted, con
 {
     // persistent-ish grid: a multiple of the SM count, never more warps than sequence blocks
     const int blocks_needed = (n + PACK_SEQS * 8 - 1) / (PACK_SEQS * 8);
-    int grid = 148 * 3;   // 78 registers -> 3 resident CTAs per SM; every warp loops over its blocks
+    int grid = 148 * 4;   // 64 registers -> 4 resident CTAs per SM; every warp loops over its blocks
     if (grid > blocks_needed) grid = blocks_needed;
     if (grid < 1) grid = 1;
     pack_kernel<<<grid, 256, 0, st>>>(ascii, src_off_sorted, order, seq_off, seq_len, n, codes, err_word);
