@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """K7 (alignment statistics without traceback) throughput on config-3 domains: GCUPS over a
-random pair list, CUDA events on the launch stream, bit-exact spot check against the oracle.
+random pair list, CUDA events on the launch stream (parity is tests/test_gpu_parity.py's job).
 
     python tools/bench_stats.py [--pairs 200000] [--mode local]
 """
@@ -46,16 +46,9 @@ def main():
         torch.cuda.synchronize()
         ms.append(e0.elapsed_time(e1))
     t = float(np.median(ms))
-    import oracle
-    k = min(2000, args.pairs)
-    seqs = col.sequences()
-    want = oracle.stats_list(seqs, pi[:k], pj[:k], mode=oracle.MODE_LOCAL if args.mode == "local" else oracle.MODE_GLOBAL)
-    got = out[:k].cpu().numpy()
-    ok = bool((got == np.stack([want[f] for f in oracle.STATS_DTYPE.names], axis=1)).all())
     print(json.dumps({"stage": "K7 gotoh_stats_kernel (includes the host-side index translation of the pair list)",
                       "mode": args.mode, "pairs": args.pairs, "cells": cells, "ms": t,
-                      "gcups": cells / (t * 1e-3) / 1e9, "pairs_per_s": args.pairs / (t * 1e-3),
-                      "bit_exact_vs_oracle_first_pairs": ok}))
+                      "gcups": cells / (t * 1e-3) / 1e9, "pairs_per_s": args.pairs / (t * 1e-3)}))
 
 
 if __name__ == "__main__":
