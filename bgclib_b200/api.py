@@ -170,7 +170,8 @@ def domain_pair_scores(source, *, database=None, mode="local", matrix="BLOSUM62"
 
 def bgc_similarity(source, *, database=None, matrix="BLOSUM62", open_gap_score=-12, extend_gap_score=-1,
                    unit="domain", cbp_only=True, alias=None, domain_types=None, same_type_only=True,
-                   bgc_ids=None, device=None, return_device=False) -> BGCSimilarity:
+                   bgc_ids=None, device=None, return_device=False, rounds=1, checkpoint=None,
+                   _stop_after_rounds=None) -> BGCSimilarity:
     """BGC x BGC similarity from local domain-pair scores:
 
         rowbest[d,b] = max{ s(d,e) : e in b, type(e) == type(d) }      (0 if none)
@@ -183,6 +184,13 @@ def bgc_similarity(source, *, database=None, matrix="BLOSUM62", open_gap_score=-
     ``bgc_ids`` fixes the row order (ids absent from ``source`` get zero rows).
     ``database``: a second collection — rows are the BGCs of ``source``, columns the BGCs of
     ``database``; only query x database domain pairs (and self pairs) are aligned.
+
+    Resumable runs (tiles are independent and max is idempotent): ``rounds`` > 1 scores this
+    rank's share of the tile list in that many equal parts; with ``checkpoint`` (a path; one file
+    per rank) the partial ``rowbest`` / self scores and the list of finished rounds are written
+    after every round and a later call on the same input and parameters continues after the last
+    finished round.  The reference's own resume idiom is the pickled collection plus the
+    ``attempted_domain_prediction`` flag (BGCtoolkit.py:552-560).
     """
     batch = _as_batch(source, unit, cbp_only, alias, domain_types)
     if database is not None:
@@ -211,10 +219,27 @@ def bgc_similarity(source, *, database=None, matrix="BLOSUM62", open_gap_score=-
     eng.set_scoring(matrix, open_gap_score, extend_gap_score, "local")
     dist, rank, world = _dist()
     eng.pack(batch.sequences, type_of_seq=batch.type_of_seq, bgc_of_seq=bgc_of, n_bgc=B)
-    plan = eng.plan(same_type_only=same_type_only, rank=rank, world=world)
     rowbest = torch.zeros((n, B), dtype=torch.int32, device=eng.tdev)
     selfsc = torch.zeros((n,), dtype=torch.int32, device=eng.tdev)
-    eng.score(rowbest=rowbest, selfsc=selfsc, type_check=False)
+    rounds = max(1, int(rounds))
+    ckpt = _Checkpoint(checkpoint, rank, batch, bgc_of, B, matrix, open_gap_score, extend_gap_score,
+                       same_type_only, rounds, world) if checkpoint is not None else None
+    done = set()
+    if ckpt is not None:
+        done = ckpt.load_into(rowbest, selfsc)
+    plan = None
+    for r in range(rounds):
+        # round r of this rank = virtual rank (rank * rounds + r) of (world * rounds)
+        part = eng.plan(same_type_only=same_type_only, rank=rank * rounds + r, world=world * rounds)
+        plan = part if plan is None else {k: (plan[k] + part[k] if k in _PLAN_SUMS else part[k]) for k in part}
+        if r in done:
+            continue
+        eng.score(rowbest=rowbest, selfsc=selfsc, type_check=False)
+        done.add(r)
+        if ckpt is not None:
+            ckpt.save(rowbest, selfsc, done)
+        if _stop_after_rounds is not None and len(done) >= _stop_after_rounds:
+            raise KeyboardInterrupt(f"stopped after {len(done)} of {rounds} rounds (test hook)")
     if dist is not None:
         dist.all_reduce(rowbest, op=dist.ReduceOp.MAX)
         dist.all_reduce(selfsc, op=dist.ReduceOp.MAX)
@@ -223,6 +248,45 @@ def bgc_similarity(source, *, database=None, matrix="BLOSUM62", open_gap_score=-
         return BGCSimilarity(sim, best, selfsum, ids, batch.records, plan)
     return BGCSimilarity(sim.cpu().numpy(), best.cpu().numpy(), selfsum.cpu().numpy(), ids,
                          batch.records, plan)
+
+
+_PLAN_SUMS = ("n_tiles", "n_pairs", "cells", "cells_computed", "n_fallback32")
+
+
+class _Checkpoint:
+    """Partial state of a ``bgc_similarity`` run on disk: one ``.npz`` per rank, written to a
+    temporary name and renamed, tagged with a digest of the input and of every parameter that
+    changes the result so that a stale file is never continued."""
+
+    def __init__(self, path, rank, batch, bgc_of, n_bgc, matrix, open_gap, extend_gap, same_type_only, rounds, world):
+        import hashlib
+        from pathlib import Path
+        self.path = Path(f"{path}.rank{rank}.npz")
+        h = hashlib.sha256()
+        h.update("\x00".join(batch.sequences).encode("ascii"))
+        h.update(np.ascontiguousarray(bgc_of, dtype=np.int32).tobytes())
+        h.update(np.ascontiguousarray(batch.type_of_seq, dtype=np.int32).tobytes())
+        h.update(np.ascontiguousarray(np.asarray(matrix) if not isinstance(matrix, str) else
+                                      np.frombuffer(matrix.encode(), dtype=np.uint8)).tobytes())
+        h.update(repr((n_bgc, int(open_gap), int(extend_gap), bool(same_type_only), int(rounds), int(world), int(rank))).encode())
+        self.tag = h.hexdigest()
+
+    def load_into(self, rowbest, selfsc):
+        if not self.path.exists():
+            return set()
+        z = np.load(self.path, allow_pickle=False)
+        if str(z["tag"]) != self.tag or z["rowbest"].shape != tuple(rowbest.shape):
+            return set()                      # different input or parameters: start over
+        import torch
+        rowbest.copy_(torch.from_numpy(z["rowbest"]))
+        selfsc.copy_(torch.from_numpy(z["selfsc"]))
+        return set(int(r) for r in z["done"])
+
+    def save(self, rowbest, selfsc, done):
+        tmp = self.path.with_suffix(".tmp.npz")
+        np.savez(tmp, tag=np.asarray(self.tag), rowbest=rowbest.cpu().numpy(), selfsc=selfsc.cpu().numpy(),
+                 done=np.asarray(sorted(done), dtype=np.int64))
+        tmp.replace(self.path)
 
 
 def _bgc_similarity_cross(q: DomainBatch, d: DomainBatch, matrix, open_gap_score, extend_gap_score,

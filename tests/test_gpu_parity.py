@@ -529,3 +529,22 @@ def test_shard_rows_under_a_process_group():
         dist.destroy_process_group()
     assert (full.scores == want).all() and full.rows is None
     assert part.rows == (0, len(seqs)) and (part.scores == want).all()
+
+
+def test_resumable_rounds_with_checkpoint(tmp_path, af293, ks_records):
+    """rounds + checkpoint: an interrupted run continues after the last finished round and ends
+    bit-identical to a single pass; a changed parameter invalidates the file."""
+    col = _af293_collection(af293, ks_records)
+    whole = bgc_similarity(col)
+    ck = tmp_path / "run"
+    with pytest.raises(KeyboardInterrupt):
+        bgc_similarity(col, rounds=5, checkpoint=ck, _stop_after_rounds=2)
+    z = np.load(f"{ck}.rank0.npz")
+    assert sorted(z["done"].tolist()) == [0, 1]
+    part = bgc_similarity(col, rounds=5, checkpoint=ck)
+    assert (part.best == whole.best).all() and (part.sim == whole.sim).all()
+    assert part.plan["n_pairs"] == whole.plan["n_pairs"] and part.plan["cells"] == whole.plan["cells"]
+    assert sorted(np.load(f"{ck}.rank0.npz")["done"].tolist()) == [0, 1, 2, 3, 4]
+    # other gap scores: the old file is ignored, not continued
+    other = bgc_similarity(col, rounds=5, checkpoint=ck, open_gap_score=-11)
+    assert (other.best == bgc_similarity(col, open_gap_score=-11).best).all()

@@ -195,3 +195,58 @@ def test_stats_empty_local_alignment_and_limits():
     assert _s(st) == dict(score=0, identities=0, columns=0, q_start=-1, q_end=-1, s_start=-1, s_end=-1, gaps=0)
     with pytest.raises(ValueError):
         oracle.stats_list(["A" * 32768, "A"], [0], [1])
+
+
+# ---- property tests (hypothesis) over random sequences, incl. the ambiguity letters -------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+_seq = st.text(alphabet=oracle.ALPHABET, min_size=1, max_size=40)
+_gaps = st.sampled_from([(-12, -1), (-11, -1), (-5, -2), (-3, -3), (-1, 0), (0, 0)])
+
+
+@settings(max_examples=150, deadline=None)
+@given(a=_seq, b=_seq, gaps=_gaps)
+def test_properties_of_the_score(a, b, gaps):
+    o, e = gaps
+    loc = oracle.score(a, b, mode=oracle.MODE_LOCAL, open_gap=o, extend_gap=e)
+    glo = oracle.score(a, b, mode=oracle.MODE_GLOBAL, open_gap=o, extend_gap=e)
+    assert loc == oracle.score(b, a, mode=oracle.MODE_LOCAL, open_gap=o, extend_gap=e)      # symmetry
+    assert glo == oracle.score(b, a, mode=oracle.MODE_GLOBAL, open_gap=o, extend_gap=e)
+    assert loc >= 0 and loc >= glo                                                          # local >= global
+    assert loc == oracle.score_3state(a, b, mode=oracle.MODE_LOCAL, open_gap=o, extend_gap=e)
+    assert glo == oracle.score_3state(a, b, mode=oracle.MODE_GLOBAL, open_gap=o, extend_gap=e)
+    assert float(loc) == gotoh_py.score(a, b, "local", o, e) and float(glo) == gotoh_py.score(a, b, "global", o, e)
+    # appending a residue cannot lower the local score; reversing both sequences keeps both scores
+    assert oracle.score(a + "W", b, mode=oracle.MODE_LOCAL, open_gap=o, extend_gap=e) >= loc
+    assert oracle.score(a[::-1], b[::-1], mode=oracle.MODE_GLOBAL, open_gap=o, extend_gap=e) == glo
+    assert oracle.score(a[::-1], b[::-1], mode=oracle.MODE_LOCAL, open_gap=o, extend_gap=e) == loc
+
+
+@settings(max_examples=60, deadline=None)
+@given(a=_seq, b=_seq)
+def test_properties_of_the_statistics(a, b):
+    for mode, cm in (("local", oracle.MODE_LOCAL), ("global", oracle.MODE_GLOBAL)):
+        s = _s(oracle.stats_list([a, b], [0], [1], mode=cm)[0])
+        assert s["score"] == oracle.score(a, b, mode=cm)
+        assert 0 <= s["identities"] <= s["columns"] - s["gaps"] <= min(len(a), len(b)) or s["columns"] == 0
+        if s["columns"]:
+            qa, sb = a[s["q_start"]:s["q_end"]], b[s["s_start"]:s["s_end"]]
+            # the reported window alone reproduces the score (global alignment of the two windows)
+            assert oracle.score(qa, sb, mode=oracle.MODE_GLOBAL) >= s["score"] or mode == "global"
+            assert oracle.score(qa, sb, mode=cm) == s["score"]
+
+
+# ---- opt-in: the real Biopython aligner, if it is ever importable where the tests run -----------
+def test_against_biopython_if_available(ks_records):
+    Align = pytest.importorskip("Bio.Align", reason="Biopython is not installed in this image (SURVEY.md F5)")
+    from Bio.Align import substitution_matrices
+    seqs = [r["sequence"] for r in ks_records]
+    for mode, cm in (("local", oracle.MODE_LOCAL), ("global", oracle.MODE_GLOBAL)):
+        al = Align.PairwiseAligner()
+        al.mode = mode
+        al.substitution_matrix = substitution_matrices.load("BLOSUM62")
+        al.open_gap_score, al.extend_gap_score = -12, -1
+        want = oracle.all_pairs(seqs, mode=cm)
+        for i in range(len(seqs)):
+            for j in range(i, len(seqs)):
+                assert al.score(seqs[i], seqs[j]) == float(want[i, j])
