@@ -742,8 +742,9 @@ int bgca_score(bgca_engine *e, int32_t *scores, int32_t *rowbest, int32_t *selfs
 // ORIGINAL-space device pair lists -> SORTED-space lists in e->d_pq / e->d_ps (lists are small
 // on these explicit-pair paths, so the translation runs on the host)
 static int stage_pair_list(bgca_engine *e, const int32_t *pi, const int32_t *pj, int64_t npairs,
-                           int max_len_allowed, const char *who, cudaStream_t st)
+                           int max_len_allowed, const char *who, cudaStream_t st, int *max_len_seen = nullptr)
 {
+    int longest = 0;
     std::vector<int32_t> hi(npairs), hj(npairs);
     CUDA_TRY(cudaMemcpyAsync(hi.data(), pi, sizeof(int32_t) * npairs, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(hj.data(), pj, sizeof(int32_t) * npairs, cudaMemcpyDeviceToHost, st));
@@ -753,6 +754,7 @@ static int stage_pair_list(bgca_engine *e, const int32_t *pi, const int32_t *pj,
             return fail(BGCA_ERR_INVALID, std::string(who) + ": index out of range");
         hi[k] = e->inv_order[hi[k]];
         hj[k] = e->inv_order[hj[k]];
+        longest = std::max(longest, std::max(e->len[hi[k]], e->len[hj[k]]));
         if (e->len[hi[k]] > max_len_allowed || e->len[hj[k]] > max_len_allowed)
             return fail(BGCA_ERR_RANGE, std::string(who) + ": sequence longer than " +
                                             std::to_string(max_len_allowed) + " residues");
@@ -762,6 +764,7 @@ static int stage_pair_list(bgca_engine *e, const int32_t *pi, const int32_t *pj,
     CUDA_TRY(cudaMemcpyAsync(e->d_pq.p, hi.data(), sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(e->d_ps.p, hj.data(), sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (max_len_seen) *max_len_seen = longest;
     return BGCA_OK;
 }
 
@@ -789,8 +792,11 @@ int bgca_pair_stats(bgca_engine *e, const int32_t *pi, const int32_t *pj, int64_
     if (npairs == 0) return BGCA_OK;
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(e->device));
-    int rc = stage_pair_list(e, pi, pj, npairs, 32767, "bgca_pair_stats", st);
+    int longest = 0;
+    int rc = stage_pair_list(e, pi, pj, npairs, 32767, "bgca_pair_stats", st, &longest);
     if (rc != BGCA_OK) return rc;
+    // every protein domain fits the one-word tuple; longer sequences take the 96-bit one
+    const int compact = (longest <= 1023 && e->max_abs_sub * 1023 < (1 << 21) && -e->open < 1000 && -e->extend < 1000);
     ScoreParams p;
     fill_params(e, p, nullptr, nullptr, nullptr, 0);
     int max_len = 0;
@@ -801,7 +807,7 @@ int bgca_pair_stats(bgca_engine *e, const int32_t *pi, const int32_t *pj, int64_
         grid = (int)std::max<long long>(1, (npairs + warps_per_cta - 1) / warps_per_cta);
     const int stride = (max_len + 3) & ~3;
     CUDA_TRY(e->d_scratch_st.reserve((size_t)grid * warps_per_cta * 2 * stride));
-    CUDA_TRY(launch_stats(e->mode, p, e->d_pq.p, e->d_ps.p, npairs, e->d_scratch_st.p, stride, out, grid, st));
+    CUDA_TRY(launch_stats(e->mode, compact, p, e->d_pq.p, e->d_ps.p, npairs, e->d_scratch_st.p, stride, out, grid, st));
     e->last_launches = 1;
     return BGCA_OK;
 }

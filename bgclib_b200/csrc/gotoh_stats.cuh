@@ -23,25 +23,98 @@ namespace bgca {
 constexpr int KS = 8;
 constexpr int PASS_ST = 32 * KS;
 
+// Wide tuple: any length up to 32767.
 struct Tup {
     long long k;
     uint32_t p;
+    static __device__ __forceinline__ Tup zero(int i, int j) { return Tup{65535LL, ((uint32_t)i << 16) | (uint32_t)j}; }
+    static __device__ __forceinline__ Tup neg() { return Tup{(long long)(-(1 << 28)) * 4294967296LL + 65535, 0u}; }
+    static __device__ __forceinline__ long long delta(int score, int ident)
+    {
+        return (long long)score * 4294967296LL + (long long)(ident << 16) - 1;
+    }
+    // a gap of `len` >= 1 residues from the corner (global boundary)
+    static __device__ __forceinline__ Tup edge(int open, int ext, int len)
+    {
+        return Tup{(long long)(open + (len - 1) * ext) * 4294967296LL + (65535 - len), 0u};
+    }
+    __device__ __forceinline__ bool gt(const Tup &o) const { return k > o.k || (k == o.k && p > o.p); }
+    __device__ __forceinline__ bool same(const Tup &o) const { return k == o.k && p == o.p; }
+    __device__ __forceinline__ Tup shfl_up() const
+    {
+        return Tup{__shfl_up_sync(0xFFFFFFFFu, k, 1), __shfl_up_sync(0xFFFFFFFFu, p, 1)};
+    }
+    __device__ __forceinline__ Tup shfl_xor(int off) const
+    {
+        return Tup{__shfl_xor_sync(0xFFFFFFFFu, k, off), __shfl_xor_sync(0xFFFFFFFFu, p, off)};
+    }
+    __device__ __forceinline__ Tup shfl(int src) const
+    {
+        return Tup{__shfl_sync(0xFFFFFFFFu, k, src), __shfl_sync(0xFFFFFFFFu, p, src)};
+    }
+    __device__ __forceinline__ int score() const { return (int)(k >> 32); }
+    __device__ __forceinline__ int identities() const { return (int)((k >> 16) & 0xFFFF); }
+    __device__ __forceinline__ int columns() const { return 65535 - (int)(k & 0xFFFF); }
+    __device__ __forceinline__ int q_start() const { return (int)(p >> 16); }
+    __device__ __forceinline__ int s_start() const { return (int)(p & 0xFFFF); }
+    __device__ __forceinline__ uint4 park_lo(const Tup &f) const
+    {
+        return make_uint4((uint32_t)k, (uint32_t)((unsigned long long)k >> 32), p, (uint32_t)f.k);
+    }
+    __device__ __forceinline__ uint4 park_hi(const Tup &f) const
+    {
+        return make_uint4((uint32_t)((unsigned long long)f.k >> 32), f.p, 0u, 0u);
+    }
+    static __device__ __forceinline__ void unpark(const uint4 &b0, const uint4 &b1, Tup &h, Tup &f)
+    {
+        h = Tup{(long long)(((unsigned long long)b0.y << 32) | b0.x), b0.z};
+        f = Tup{(long long)(((unsigned long long)b1.x << 32) | b0.w), b1.y};
+    }
 };
 
-__device__ __forceinline__ bool tup_gt(const Tup &a, const Tup &b) { return a.k > b.k || (a.k == b.k && a.p > b.p); }
-__device__ __forceinline__ Tup tup_max(const Tup &a, const Tup &b) { return tup_gt(b, a) ? b : a; }
-__device__ __forceinline__ Tup tup_add(Tup a, long long d) { a.k += d; return a; }
-__device__ __forceinline__ Tup tup_zero(int i, int j) { return Tup{65535LL, ((uint32_t)i << 16) | (uint32_t)j}; }
-__device__ __forceinline__ long long col_delta(int score, int ident)
-{
-    return (long long)score * 4294967296LL + (long long)(ident << 16) - 1;
-}
-__device__ __forceinline__ Tup tup_shfl_up(const Tup &a)
-{
-    return Tup{__shfl_up_sync(0xFFFFFFFFu, a.k, 1), __shfl_up_sync(0xFFFFFFFFu, a.p, 1)};
-}
+// Compact tuple for sequences of at most 1023 residues (every protein domain): the same
+// lexicographic order (score, identities, -columns, q_start, s_start) in ONE 64-bit integer —
+// score:23 | identities:10 | 2047-columns:11 | q_start:10 | s_start:10 — so a max is one 64-bit
+// compare and an add touches one value.
+struct Tup64 {
+    long long k;
+    static __device__ __forceinline__ Tup64 zero(int i, int j) { return Tup64{(2047LL << 20) | ((long long)i << 10) | j}; }
+    static __device__ __forceinline__ Tup64 neg() { return Tup64{((long long)(-(1 << 20)) << 41) + (2047LL << 20)}; }
+    static __device__ __forceinline__ long long delta(int score, int ident)
+    {
+        return ((long long)score << 41) + ((long long)ident << 31) - (1LL << 20);
+    }
+    static __device__ __forceinline__ Tup64 edge(int open, int ext, int len)
+    {
+        return Tup64{((long long)(open + (len - 1) * ext) << 41) + ((long long)(2047 - len) << 20)};
+    }
+    __device__ __forceinline__ bool gt(const Tup64 &o) const { return k > o.k; }
+    __device__ __forceinline__ bool same(const Tup64 &o) const { return k == o.k; }
+    __device__ __forceinline__ Tup64 shfl_up() const { return Tup64{__shfl_up_sync(0xFFFFFFFFu, k, 1)}; }
+    __device__ __forceinline__ Tup64 shfl_xor(int off) const { return Tup64{__shfl_xor_sync(0xFFFFFFFFu, k, off)}; }
+    __device__ __forceinline__ Tup64 shfl(int src) const { return Tup64{__shfl_sync(0xFFFFFFFFu, k, src)}; }
+    __device__ __forceinline__ int score() const { return (int)(k >> 41); }
+    __device__ __forceinline__ int identities() const { return (int)((k >> 31) & 1023); }
+    __device__ __forceinline__ int columns() const { return 2047 - (int)((k >> 20) & 2047); }
+    __device__ __forceinline__ int q_start() const { return (int)((k >> 10) & 1023); }
+    __device__ __forceinline__ int s_start() const { return (int)(k & 1023); }
+    __device__ __forceinline__ uint4 park_lo(const Tup64 &f) const
+    {
+        return make_uint4((uint32_t)k, (uint32_t)((unsigned long long)k >> 32), (uint32_t)f.k,
+                          (uint32_t)((unsigned long long)f.k >> 32));
+    }
+    __device__ __forceinline__ uint4 park_hi(const Tup64 &) const { return make_uint4(0u, 0u, 0u, 0u); }
+    static __device__ __forceinline__ void unpark(const uint4 &b0, const uint4 &, Tup64 &h, Tup64 &f)
+    {
+        h = Tup64{(long long)(((unsigned long long)b0.y << 32) | b0.x)};
+        f = Tup64{(long long)(((unsigned long long)b0.w << 32) | b0.z)};
+    }
+};
 
-template <int MODE>
+template <typename T> __device__ __forceinline__ T tup_max(const T &a, const T &b) { return b.gt(a) ? b : a; }
+template <typename T> __device__ __forceinline__ T tup_add(T a, long long d) { a.k += d; return a; }
+
+template <int MODE, typename T>
 __global__ void __launch_bounds__(CTA_THREADS)
 gotoh_stats_kernel(const ScoreParams p, const int32_t *__restrict__ pq, const int32_t *__restrict__ ps,
                    long long npairs, uint4 *scratch, int scratch_stride, bgca_alnstats *__restrict__ out)
@@ -56,38 +129,35 @@ gotoh_stats_kernel(const ScoreParams p, const int32_t *__restrict__ pq, const in
     const long long w = (long long)blockIdx.x * (CTA_THREADS / 32) + (threadIdx.x >> 5);
     const long long nw = (long long)gridDim.x * (CTA_THREADS / 32);
     uint4 *bnd = scratch + w * 2 * (long long)scratch_stride;   // two uint4 per subject column
-    const long long d_open = col_delta(p.open, 0), d_ext = col_delta(p.extend, 0);
-    const Tup NEG{(long long)(-(1 << 28)) * 4294967296LL + 65535, 0u};
-
+    const long long d_open = T::delta(p.open, 0), d_ext = T::delta(p.extend, 0);
+    const T NEG = T::neg();
     // H[r+1][0] and H[0][j+1] of the global boundary: a gap of r+1 (j+1) columns from the corner
-    auto edge = [&](int len) {   // len >= 1 gapped residues
-        return Tup{(long long)(p.open + (len - 1) * p.extend) * 4294967296LL + (65535 - len), 0u};
-    };
+    auto edge = [&](int len) { return T::edge(p.open, p.extend, len); };
 
     for (long long pair = w; pair < npairs; pair += nw) {
         const int q = pq[pair], s = ps[pair];
         const int La = p.seq_len[q], Ls = p.seq_len[s];
         const uint8_t *qp = p.codes + p.seq_off[q];
         const uint8_t *sp = p.codes + p.seq_off[s];
-        Tup best = tup_zero(0, 0);          // best of this lane over all passes
+        T best = T::zero(0, 0);             // best of this lane over all passes
         uint32_t best_end = 0;              // s_end << 16 | q_end (DP corner), smaller wins ties
-        Tup cap = tup_zero(0, 0);
+        T cap = T::zero(0, 0);
         const int npass = (La + PASS_ST - 1) / PASS_ST;
 
         for (int pass = 0; pass < npass; ++pass) {
             const int i0 = pass * PASS_ST + lane * KS;
             int qrow[KS];
-            Tup Hp[KS], Eh[KS];
+            T Hp[KS], Eh[KS];
 #pragma unroll
             for (int k = 0; k < KS; ++k) {
                 const int r = i0 + k;
                 qrow[k] = (r < La) ? (int)qp[r] * NSYM : -NSYM;
-                Hp[k] = LOCAL ? tup_zero(r + 1, 0) : edge(r + 1);
+                Hp[k] = LOCAL ? T::zero(r + 1, 0) : edge(r + 1);
                 Eh[k] = NEG;
             }
-            Tup hin_prev = LOCAL ? tup_zero(i0, 0) : (i0 == 0 ? tup_zero(0, 0) : edge(i0));
-            Tup h_out = NEG, f_out = NEG;
-            Tup pbest = tup_zero(0, 0);     // best of this pass (visited column-major: strict > keeps
+            T hin_prev = LOCAL ? T::zero(i0, 0) : (i0 == 0 ? T::zero(0, 0) : edge(i0));
+            T h_out = NEG, f_out = NEG;
+            T pbest = T::zero(0, 0);        // best of this pass (visited column-major: strict > keeps
             uint32_t pbest_end = 0;         // the smallest s_end, then the smallest q_end)
             int j = -lane;
             int c_next = ((unsigned)j < (unsigned)Ls) ? (int)__ldg(sp + j) : 0;
@@ -96,24 +166,23 @@ gotoh_stats_kernel(const ScoreParams p, const int32_t *__restrict__ pq, const in
             const bool park = (pass + 1 < npass);
 
             for (int tau = 0; tau < Ls + 31; ++tau, ++j) {
-                Tup h_in = tup_shfl_up(h_out);
-                Tup f_in = tup_shfl_up(f_out);
+                T h_in = h_out.shfl_up();
+                T f_in = f_out.shfl_up();
                 const int c = c_next;
                 c_next = ((unsigned)(j + 1) < (unsigned)Ls) ? (int)__ldg(sp + j + 1) : 0;
                 if (lane == 0) {
                     if (pass == 0) {
-                        h_in = LOCAL ? tup_zero(0, j + 1) : edge(j + 1);
+                        h_in = LOCAL ? T::zero(0, j + 1) : edge(j + 1);
                         f_in = NEG;
                     } else {
-                        h_in = Tup{(long long)(((unsigned long long)b0.y << 32) | b0.x), b0.z};
-                        f_in = Tup{(long long)(((unsigned long long)b1.x << 32) | b0.w), b1.y};
+                        T::unpark(b0, b1, h_in, f_in);
                         if (j + 1 < Ls) { b0 = __ldcg(bnd + 2 * (j + 1)); b1 = __ldcg(bnd + 2 * (j + 1) + 1); }
                     }
                 }
                 if ((unsigned)j < (unsigned)Ls) {
-                    Tup diag = hin_prev;
+                    T diag = hin_prev;
                     hin_prev = h_in;
-                    Tup up = h_in, F = f_in;
+                    T up = h_in, F = f_in;
                     const int crow = c * NSYM;
 #pragma unroll
                     for (int k = 0; k < KS; ++k) {
@@ -121,11 +190,11 @@ gotoh_stats_kernel(const ScoreParams p, const int32_t *__restrict__ pq, const in
                         const int sc = real ? (int)ssub[qrow[k] + c] : 0;
                         Eh[k] = tup_max(tup_add(Eh[k], d_ext), tup_add(Hp[k], d_open));
                         F = tup_max(tup_add(F, d_ext), tup_add(up, d_open));
-                        Tup h = tup_add(diag, col_delta(sc, qrow[k] == crow));
+                        T h = tup_add(diag, T::delta(sc, qrow[k] == crow));
                         h = tup_max(tup_max(h, Eh[k]), F);
                         if (LOCAL) {
-                            h = tup_max(h, tup_zero(i0 + k + 1, j + 1));
-                            if (real && tup_gt(h, pbest)) {
+                            h = tup_max(h, T::zero(i0 + k + 1, j + 1));
+                            if (real && h.gt(pbest)) {
                                 pbest = h;
                                 pbest_end = ((uint32_t)(j + 1) << 16) | (uint32_t)(i0 + k + 1);
                             }
@@ -137,9 +206,8 @@ gotoh_stats_kernel(const ScoreParams p, const int32_t *__restrict__ pq, const in
                     h_out = up;
                     f_out = F;
                     if (park && lane == 31) {
-                        __stcg(bnd + 2 * j, make_uint4((uint32_t)up.k, (uint32_t)((unsigned long long)up.k >> 32), up.p,
-                                                       (uint32_t)F.k));
-                        __stcg(bnd + 2 * j + 1, make_uint4((uint32_t)((unsigned long long)F.k >> 32), F.p, 0u, 0u));
+                        __stcg(bnd + 2 * j, up.park_lo(F));
+                        __stcg(bnd + 2 * j + 1, up.park_hi(F));
                     }
                     if (!LOCAL && j == Ls - 1) {
 #pragma unroll
@@ -151,7 +219,7 @@ gotoh_stats_kernel(const ScoreParams p, const int32_t *__restrict__ pq, const in
             if (LOCAL) {
                 // passes are visited in row order: an equal (key, start) of a later pass wins only
                 // with a smaller s_end
-                if (tup_gt(pbest, best) || (pbest.k == best.k && pbest.p == best.p && pbest_end < best_end)) {
+                if (pbest.gt(best) || (pbest.same(best) && pbest_end < best_end)) {
                     best = pbest;
                     best_end = pbest_end;
                 }
@@ -162,29 +230,29 @@ gotoh_stats_kernel(const ScoreParams p, const int32_t *__restrict__ pq, const in
         if (LOCAL) {
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
-                const Tup o{__shfl_xor_sync(FULL, best.k, off), __shfl_xor_sync(FULL, best.p, off)};
+                const T o = best.shfl_xor(off);
                 const uint32_t oe = __shfl_xor_sync(FULL, best_end, off);
-                if (tup_gt(o, best) || (o.k == best.k && o.p == best.p && oe < best_end)) {
+                if (o.gt(best) || (o.same(best) && oe < best_end)) {
                     best = o;
                     best_end = oe;
                 }
             }
         } else {
             const int src = ((La - 1) % PASS_ST) / KS;
-            best = Tup{__shfl_sync(FULL, cap.k, src), __shfl_sync(FULL, cap.p, src)};
+            best = cap.shfl(src);
             best_end = ((uint32_t)Ls << 16) | (uint32_t)La;
         }
         if (lane == 0) {
             bgca_alnstats r;
-            r.score = (int32_t)(best.k >> 32);
-            r.identities = (int32_t)((best.k >> 16) & 0xFFFF);
-            r.columns = 65535 - (int32_t)(best.k & 0xFFFF);
+            r.score = best.score();
+            r.identities = best.identities();
+            r.columns = best.columns();
             if (r.columns == 0) {
                 r.q_start = r.q_end = r.s_start = r.s_end = -1;
                 r.gaps = 0;
             } else {
-                r.q_start = (int32_t)(best.p >> 16);
-                r.s_start = (int32_t)(best.p & 0xFFFF);
+                r.q_start = best.q_start();
+                r.s_start = best.s_start();
                 r.q_end = (int32_t)(best_end & 0xFFFF);
                 r.s_end = (int32_t)(best_end >> 16);
                 r.gaps = 2 * r.columns - (r.q_end - r.q_start) - (r.s_end - r.s_start);

@@ -23,7 +23,7 @@ cudaError_t launch_s32(int mode, const ScoreParams &p, const int32_t *pq, const 
                        int grid, cudaStream_t st);
 
 // K7 (stats.cu)
-cudaError_t launch_stats(int mode, const ScoreParams &p, const int32_t *pq, const int32_t *ps,
+cudaError_t launch_stats(int mode, int compact, const ScoreParams &p, const int32_t *pq, const int32_t *ps,
                          long long npairs, uint4 *scratch, int scratch_stride, bgca_alnstats *out,
                          int grid, cudaStream_t st);
 

@@ -4,16 +4,21 @@
 
 namespace bgca {
 
-cudaError_t launch_stats(int mode, const ScoreParams &p, const int32_t *pq, const int32_t *ps,
+// compact != 0: every sequence in the pair list is at most 1023 residues long (Tup64 fits)
+cudaError_t launch_stats(int mode, int compact, const ScoreParams &p, const int32_t *pq, const int32_t *ps,
                          long long npairs, uint4 *scratch, int scratch_stride, bgca_alnstats *out,
                          int grid, cudaStream_t st)
 {
-    if (mode == BGCA_MODE_LOCAL)
-        gotoh_stats_kernel<BGCA_MODE_LOCAL><<<grid, CTA_THREADS, 0, st>>>(p, pq, ps, npairs, scratch,
-                                                                         scratch_stride, out);
-    else
-        gotoh_stats_kernel<BGCA_MODE_GLOBAL><<<grid, CTA_THREADS, 0, st>>>(p, pq, ps, npairs, scratch,
-                                                                          scratch_stride, out);
+#define BGCA_LAUNCH_STATS(M, T) \
+    gotoh_stats_kernel<M, T><<<grid, CTA_THREADS, 0, st>>>(p, pq, ps, npairs, scratch, scratch_stride, out)
+    if (mode == BGCA_MODE_LOCAL) {
+        if (compact) BGCA_LAUNCH_STATS(BGCA_MODE_LOCAL, Tup64);
+        else BGCA_LAUNCH_STATS(BGCA_MODE_LOCAL, Tup);
+    } else {
+        if (compact) BGCA_LAUNCH_STATS(BGCA_MODE_GLOBAL, Tup64);
+        else BGCA_LAUNCH_STATS(BGCA_MODE_GLOBAL, Tup);
+    }
+#undef BGCA_LAUNCH_STATS
     return cudaGetLastError();
 }
 

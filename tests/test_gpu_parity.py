@@ -478,7 +478,7 @@ def test_stats_ks_golden(ks_records, mode):
 
 
 @pytest.mark.parametrize("mode", ["local", "global"])
-@pytest.mark.parametrize("lo,hi", [(1, 12), (30, 90), (200, 300), (250, 530), (700, 1100)])
+@pytest.mark.parametrize("lo,hi", [(1, 12), (30, 90), (200, 300), (250, 530), (700, 1100), (1023, 1023), (1020, 1026)])
 def test_stats_random_bit_exact(mode, lo, hi):
     """Single-pass and multi-pass (query > 256 rows) sweeps, ties, B/Z/X letters, empty alignments."""
     from bgclib_b200 import domain_pair_stats
