@@ -157,7 +157,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--probe", action="store_true", help="also run the DPX issue-rate microbenchmark")
+    ap.add_argument("--probe", action="store_true", help="(default at N=1) run the DPX issue-rate microbenchmark")
+    ap.add_argument("--no-probe", action="store_true", help="skip the DPX issue-rate microbenchmark")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -347,12 +348,14 @@ def main():
                                         "the scattered 4-byte score stores cost ~8x in 32 B sectors, at 0.03 % of HBM bandwidth")
         except Exception:
             pass
-        if args.probe:
+        if (args.probe or world == 1) and not args.no_probe:
             probe = bgclib_b200.dpx_probe(local_rank)
             roofline["dpx_probe_lane_ops_per_clk_sm"] = probe
-            meas_peak = n_sm * probe["cell_mix_s16x2"] * probe["sm_mhz"] * 1e6 / 1e12
-            roofline["peak_measured_cell_mix"] = meas_peak
-            roofline["frac_of_measured_cell_mix"] = achieved * (5.5 / 6.0) / meas_peak
+            # the bare DP instruction stream of this kernel (no loads, shuffles, loop): the measured
+            # issue-rate ceiling for this op mix, as GCUPS at the clock observed during the run
+            stream_gcups = n_sm * (probe["cell_mix_s16x2"] / 5.5) * 2 * sm_mhz * 1e6 / 1e9
+            roofline["peak_measured_dp_stream_gcups"] = stream_gcups
+            roofline["frac_of_measured_dp_stream"] = roofline["kernel_gcups"] / stream_gcups
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             g, pps, cores, desc, _ = cpu_reference_run(col, args.cpu_seconds)

@@ -52,45 +52,46 @@ __global__ void __launch_bounds__(512) probe_kernel(uint32_t a, uint32_t seed, u
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
-// OP 8: the packed local cell recurrence exactly as in gotoh_pair16.cuh
-// (K = 8 rows, profile words from registers) — the practical ceiling of the
-// inner loop without shared-memory, shuffle or loop overhead.
-__global__ void __launch_bounds__(512) probe_cell_kernel(uint32_t ext2, uint32_t open2, uint32_t seed,
-                                                         uint32_t *sink, long long *cycles)
+// OP 8: the packed local cell recurrence exactly as in gotoh_pair16.cuh (next-T form, gap
+// scores as immediates, K = 26 rows per lane, 2 CTAs x 256 threads per SM = the occupancy of the
+// real kernel on ~420-residue queries) with all state in registers and NO shared memory,
+// shuffles, token handling or loop control beyond the step counter: the ceiling of the DP
+// instruction stream itself, which the kernel's remaining ~34 instructions per step eat into.
+constexpr int CELL_K = 26;
+constexpr int CELL_ITERS = 2048;
+__global__ void __launch_bounds__(256, 2) probe_cell_kernel(uint32_t seed, uint32_t *sink, long long *cycles)
 {
-    constexpr int K = 8;
-    uint32_t Ho[K], E[K], P[K];
+    constexpr uint32_t EXT2 = 0xFFFFFFFFu, OPEN2 = 0xFFF4FFF4u;   // (-1, -1) and (-12, -12)
+    uint32_t Tn[CELL_K], E[CELL_K], P[CELL_K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        Ho[k] = 0; E[k] = 0;
-        P[k] = (seed * (threadIdx.x + 3 + k)) & 0x00070007u;
+    for (int k = 0; k < CELL_K; ++k) {
+        Tn[k] = 0; E[k] = 0;
+        P[k] = ((seed * (threadIdx.x + 3 + k)) & 0x00070007u) + 0x000C000Cu;
     }
-    uint32_t best = 0, hin_prev = 0, h_in = seed & 0x000F000Fu, f_in = 0;
+    uint32_t best = 0, h_in = seed & 0x000F000Fu, f_in = 0;
     __syncthreads();
     const long long t0 = clock64();
 #pragma unroll 1
-    for (int it = 0; it < PROBE_ITERS; ++it) {
-        uint32_t diag = hin_prev;
-        hin_prev = h_in;
-        uint32_t up = h_in, F = f_in;
-        uint32_t h_prev = 0;
+    for (int it = 0; it < CELL_ITERS; ++it) {
+        uint32_t up = h_in, F = f_in, h_prev = 0;
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            E[k] = __viaddmax_s16x2(E[k], ext2, Ho[k]);
-            F = __viaddmax_s16x2(F, ext2, up);
-            const uint32_t tt = __vadd2(diag, P[k]);
-            const uint32_t h = __vimax3_s16x2_relu(tt, E[k], F);
-            diag = Ho[k];
-            up = __vadd2(h, open2);
-            Ho[k] = up;
+        for (int k = 0; k < CELL_K; ++k) {
+            F = __viaddmax_s16x2(F, EXT2, up);
+            const uint32_t h = __vimax3_s16x2_relu(Tn[k], E[k], F);
+            Tn[k] = __vadd2(up, P[k]);
+            up = __vadd2(h, OPEN2);
+            E[k] = __viaddmax_s16x2(E[k], EXT2, up);
             if (k & 1) best = __vimax3_s16x2(best, h_prev, h);
             h_prev = h;
         }
-        h_in = up ^ (uint32_t)it;   // keep the next step dependent on this one
+        h_in = up ^ (uint32_t)(it & 1);   // keep the next step dependent on this one
         f_in = F;
     }
     const long long t1 = clock64();
-    if (best == 0x12345678u) sink[0] = best;
+    uint32_t acc = best ^ h_in ^ f_in;
+#pragma unroll
+    for (int k = 0; k < CELL_K; ++k) acc ^= Tn[k] ^ E[k];
+    if (acc == 0x12345678u) sink[0] = acc;
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
@@ -216,9 +217,9 @@ int dpx_probe_run(int device, double *out, int n)
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0);
         cudaEventCreate(&e1);
-        probe_cell_kernel<<<grid, 512>>>(0xFFFFFFFFu, 0xFFF4FFF4u, 777u, sink, d_cycles);
+        probe_cell_kernel<<<grid, 256>>>(777u, sink, d_cycles);
         cudaEventRecord(e0);
-        probe_cell_kernel<<<grid, 512>>>(0xFFFFFFFFu, 0xFFF4FFF4u, 777u, sink, d_cycles);
+        probe_cell_kernel<<<grid, 256>>>(777u, sink, d_cycles);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms = 0.f;
@@ -226,7 +227,8 @@ int dpx_probe_run(int device, double *out, int n)
         cudaMemcpy(h_cycles, d_cycles, sizeof(long long) * grid, cudaMemcpyDeviceToHost);
         long long worst = 0;
         for (int i = 0; i < grid; ++i) worst = h_cycles[i] > worst ? h_cycles[i] : worst;
-        r[8] = 1024.0 * (8 * 5.5) * PROBE_ITERS / (double)worst;
+        // lane-ops (5.5 per cell pair) per clock per SM; cell pairs per clock per SM = r[8] / 5.5
+        r[8] = 512.0 * (CELL_K * 5.5) * CELL_ITERS / (double)worst;
         r[9] = (double)worst / (ms * 1e3);   // cycles per microsecond = MHz (kernel ~ whole event span)
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);

@@ -184,8 +184,10 @@ int bgca_last_pack_ms(bgca_engine *e, float *ms);
 /* Calibration microbenchmark: issue rate of the DPX/ALU ops
  * the DP kernels are made of.  Fills out[0..n) with lane-ops per clock per SM
  * for: 0 VIADDMNMX.S16x2, 1 VIMNMX3.S16x2, 2 VIMNMX.S16x2, 3 VIADD.16x2
- * (__vadd2), 4 IADD3, 5 IMAD, 6 PRMT, 7 VIADDMNMX (s32), 8 the 5.5-op packed
- * local cell mix (reported as lane-ops), 9 measured SM clock in MHz,
+ * (__vadd2), 4 IADD3, 5 IMAD, 6 PRMT, 7 VIADDMNMX (s32), 8 the bare instruction
+ * stream of the packed local cell (5.5 ops per 2 cells, K = 26, the kernel's
+ * occupancy; reported as lane-ops: cell pairs per clock per SM = value / 5.5),
+ * 9 measured SM clock in MHz,
  * 10-13 two-op mixes (VIADDMNMX+VIADD.16x2, VIADDMNMX+IMAD, VIMNMX3+VIADD.16x2,
  * VIADD.16x2+IMAD: > 64 means the two ops issue to different pipes),
  * 14-17 dependent-chain latency in cycles (VIADDMNMX, VIMNMX3, VIADD.16x2, and
