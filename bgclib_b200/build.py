@@ -30,7 +30,7 @@ UNITS = [("bgca_api.o", "bgca_api.cu", []),
          ("pack_reduce.o", "pack_reduce.cu", []),
          ("stats.o", "stats.cu", []),
          ("dpx_probe.o", "dpx_probe.cu", [])]
-for g in (8, 16, 32):
+for g in (4, 8, 16, 32):
     for m in (0, 1):
         for pr in (0, 1, 2):
             UNITS.append((f"dp_g{g}_m{m}_p{pr}.o", "dp_inst.cu",

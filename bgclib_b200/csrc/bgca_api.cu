@@ -51,14 +51,16 @@ double variant_cost(int G, int K, int /*Lq*/)
     return (5.5 * K + 21.0 + (K + 3) / 4) * (double)G;
 }
 
-// BGCA_FORCE_G=8|16|32 restricts the planner to one group width (tuning aid).
+// BGCA_FORCE_G=4|8|16|32 restricts the planner to one group width (tuning aid).
 int forced_group_width()
 {
     const char *s = std::getenv("BGCA_FORCE_G");
     return s ? std::atoi(s) : 0;
 }
 
-int pick_variant(int Lq, int mode)
+// n_subjects: subjects the query pair meets in its block.  G = 4 runs 64 subject streams per CTA
+// and is only offered when there are enough subjects to keep them busy.
+int pick_variant(int Lq, int mode, int n_subjects = 1 << 30)
 {
     int best = 0;
     double best_cost = 0.0;
@@ -68,6 +70,7 @@ int pick_variant(int Lq, int mode)
     for (int v = 0; v < kNumVariants; ++v) {
         const int G = kVariants[v].G, K = kVariants[v].K;
         if (G * K < Lq || K > k_cap) continue;
+        if (G == 4 && force_g != 4 && n_subjects < 4 * (CTA_THREADS / 4)) continue;
         if (force_g && G != force_g && force_g * 32 >= Lq) continue;
         const double c = variant_cost(G, K, Lq);
         if (!best || c < best_cost) {
@@ -190,11 +193,11 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
             const int qb = (qa + 1 < tm) ? qa + 1 : -1;
             const int La = len[qa], Lb = (qb >= 0) ? len[qb] : 0;
             const int Lq = std::max(La, Lb);
-            int variant = pick_variant(Lq, mode);
-            const int G = variant >> 8;
             const int sub0 = cross_only ? tm : qa;
             const int S = te - sub0;
             if (S <= 0) continue;
+            int variant = pick_variant(Lq, mode, S);
+            const int G = variant >> 8;
             // subjects per tile: ~spg per alignment group (= subject stream) of the CTA,
             // split evenly over the row and rounded up to a whole number per group
             const int ngroups = variant ? CTA_THREADS / G : 16;
@@ -222,7 +225,7 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
                     const int Lq = std::max(La, Lb);
                     bgca_tile T{};
                     T.qa = qa; T.qb = qb; T.s_begin = qa; T.s_end = (qb >= 0 ? qb : qa) + 1;
-                    T.variant = pick_variant(Lq, mode);
+                    T.variant = pick_variant(Lq, mode, 1);
                     T.reserved = 1;
                     if (T.variant && !fits_int16(mode, max_abs_sub, open, extend, Lq, Lq)) T.variant = 0;
                     T.cells = (int64_t)(La + Lb) * (pre[T.s_end] - pre[T.s_begin]);
@@ -702,14 +705,16 @@ int bgca_score(bgca_engine *e, int32_t *scores, int32_t *rowbest, int32_t *selfs
         int grid = 0;
         const bool local = e->mode == BGCA_MODE_LOCAL;
         // [G index][mode][gap preset]; preset 0 takes the gap scores at run time
-        static const Pair16Launcher table[3][2][3] = {
+        static const Pair16Launcher table[4][2][3] = {
+            {{launch_pair16_g4_m0_p0, launch_pair16_g4_m0_p1, launch_pair16_g4_m0_p2},
+             {launch_pair16_g4_m1_p0, launch_pair16_g4_m1_p1, launch_pair16_g4_m1_p2}},
             {{launch_pair16_g8_m0_p0, launch_pair16_g8_m0_p1, launch_pair16_g8_m0_p2},
              {launch_pair16_g8_m1_p0, launch_pair16_g8_m1_p1, launch_pair16_g8_m1_p2}},
             {{launch_pair16_g16_m0_p0, launch_pair16_g16_m0_p1, launch_pair16_g16_m0_p2},
              {launch_pair16_g16_m1_p0, launch_pair16_g16_m1_p1, launch_pair16_g16_m1_p2}},
             {{launch_pair16_g32_m0_p0, launch_pair16_g32_m0_p1, launch_pair16_g32_m0_p2},
              {launch_pair16_g32_m1_p0, launch_pair16_g32_m1_p1, launch_pair16_g32_m1_p2}}};
-        const int gi = (G == 8) ? 0 : (G == 16) ? 1 : (G == 32) ? 2 : -1;
+        const int gi = (G == 4) ? 0 : (G == 8) ? 1 : (G == 16) ? 2 : (G == 32) ? 3 : -1;
         int preset = 0;
         if (e->open == -12 && e->extend == -1) preset = 1;
         else if (e->open == -11 && e->extend == -1) preset = 2;

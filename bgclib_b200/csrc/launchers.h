@@ -9,6 +9,8 @@ using Pair16Launcher = cudaError_t (*)(int K, const ScoreParams &p, int n_sm, cu
 #define BGCA_DECL_LAUNCH(G, M, P) \
     cudaError_t launch_pair16_g##G##_m##M##_p##P(int K, const ScoreParams &p, int n_sm, cudaStream_t st, int *grid_out);
 #define BGCA_DECL_LAUNCH_GM(G, M) BGCA_DECL_LAUNCH(G, M, 0) BGCA_DECL_LAUNCH(G, M, 1) BGCA_DECL_LAUNCH(G, M, 2)
+BGCA_DECL_LAUNCH_GM(4, 0)
+BGCA_DECL_LAUNCH_GM(4, 1)
 BGCA_DECL_LAUNCH_GM(8, 0)
 BGCA_DECL_LAUNCH_GM(8, 1)
 BGCA_DECL_LAUNCH_GM(16, 0)

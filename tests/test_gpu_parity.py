@@ -59,7 +59,7 @@ def test_random_lengths_bit_exact(mode, lo, hi):
     assert res.plan["n_fallback32"] == 0
 
 
-@pytest.mark.parametrize("force_g", ["8", "16", "32"])
+@pytest.mark.parametrize("force_g", ["4", "8", "16", "32"])
 def test_every_group_width(monkeypatch, force_g):
     monkeypatch.setenv("BGCA_FORCE_G", force_g)
     rng = np.random.default_rng(int(force_g))
