@@ -335,7 +335,7 @@ class DomainPairStats:
 
 def domain_pair_stats(source, pairs=None, *, mode="local", matrix="BLOSUM62", open_gap_score=-12,
                       extend_gap_score=-1, unit="domain", cbp_only=True, alias=None, domain_types=None,
-                      device=None) -> DomainPairStats:
+                      device=None, min_score=None, same_type_only=False) -> DomainPairStats:
     """Alignment-derived statistics WITHOUT traceback (identities, alignment length, start/end
     coordinates, gap columns) for selected domain pairs — what a BiG-SCAPE-style distance on the
     same domains needs (the reference holds no such code).
@@ -345,12 +345,26 @@ def domain_pair_stats(source, pairs=None, *, mode="local", matrix="BLOSUM62", op
     of (score, identities, -columns, q_start, s_start, -s_end, -q_end) over all alignments in
     ``mode`` (include/bgca.h, bgca_pair_stats), so ``score`` equals ``domain_pair_scores``' value.
     Coordinates index the domain sequence (0-based, end-exclusive, like ali_from/ali_to,
-    BGClib/BGClib.py:3222-3241)."""
+    BGClib/BGClib.py:3222-3241).
+
+    ``min_score`` (with ``pairs=None``): two stages on the device — the all-vs-all scoring kernels
+    first (optionally ``same_type_only``), then statistics only for the pairs i < j whose score
+    reaches ``min_score``: the usual shape of an identity-based distance, which is only wanted
+    for pairs that are similar at all."""
     batch = _as_batch(source, unit, cbp_only, alias, domain_types)
     n = len(batch)
     if n == 0:
         raise ValueError("no domain sequences selected")
-    if pairs is None:
+    if pairs is None and min_score is not None:
+        sc = domain_pair_scores(batch, mode=mode, matrix=matrix, open_gap_score=open_gap_score,
+                                extend_gap_score=extend_gap_score, same_type_only=same_type_only,
+                                device=device, return_device=True)
+        t = sc.scores
+        keep = t >= int(min_score)
+        if sc.computed is not None:
+            keep &= sc.computed
+        pairs = keep.triu(diagonal=1).nonzero().to("cpu").numpy()     # row-major: sorted by (i, j)
+    elif pairs is None:
         iu = np.triu_indices(n, k=1)
         pairs = np.stack(iu, axis=1)
     pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)

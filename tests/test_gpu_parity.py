@@ -548,3 +548,21 @@ def test_resumable_rounds_with_checkpoint(tmp_path, af293, ks_records):
     # other gap scores: the old file is ignored, not continued
     other = bgc_similarity(col, rounds=5, checkpoint=ck, open_gap_score=-11)
     assert (other.best == bgc_similarity(col, open_gap_score=-11).best).all()
+
+
+def test_stats_for_pairs_above_a_score():
+    """Two-stage use: all-vs-all scores, then statistics only where the score reaches a threshold."""
+    from bgclib_b200 import domain_pair_stats
+    rng = np.random.default_rng(21)
+    seqs = _related(rng, 4, 5, 60, 220) + [_rand(rng, 100) for _ in range(6)]
+    want_scores = oracle.all_pairs(seqs)
+    thr = 120
+    res = domain_pair_stats(seqs, min_score=thr)
+    iu = np.triu_indices(len(seqs), k=1)
+    sel = want_scores[iu] >= thr
+    want_pairs = np.stack(iu, axis=1)[sel]
+    assert 0 < len(want_pairs) < len(sel)                      # the threshold separates the families
+    assert (res.pairs == want_pairs).all()
+    want = oracle.stats_list(seqs, want_pairs[:, 0], want_pairs[:, 1])
+    assert (_stat_rows(res.stats) == _stat_rows(want)).all()
+    assert (res.stats["score"] >= thr).all()
