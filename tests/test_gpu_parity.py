@@ -566,3 +566,31 @@ def test_stats_for_pairs_above_a_score():
     want = oracle.stats_list(seqs, want_pairs[:, 0], want_pairs[:, 1])
     assert (_stat_rows(res.stats) == _stat_rows(want)).all()
     assert (res.stats["score"] >= thr).all()
+
+
+def test_outputs_stay_inside_their_buffers():
+    """Guard rows around every caller-owned output (compute-sanitizer is not available on the
+    pool): nothing outside the declared shapes may be written, whatever the kernel variant."""
+    import torch
+    rng = np.random.default_rng(5)
+    seqs = _related(rng, 4, 6, 20, 400) + [_rand(rng, k) for k in (1, 5, 700, 1500)]
+    n, B = len(seqs), 7
+    bgc_of = rng.integers(0, B, n).astype(np.int32)
+    eng = get_engine()
+    SENT = -123456789
+    for mode in ("local", "global"):
+        eng.set_scoring(mode=mode)
+        eng.pack(seqs, type_of_seq=np.zeros(n, np.int32), bgc_of_seq=bgc_of, n_bgc=B)
+        eng.plan()
+        big = torch.full((n + 2, n), SENT, dtype=torch.int32, device="cuda")
+        rb = torch.full((n + 2, B), SENT, dtype=torch.int32, device="cuda")
+        ss = torch.full((n + 2,), SENT, dtype=torch.int32, device="cuda")
+        big[1:n + 1].fill_(-2**31)
+        rb[1:n + 1].zero_()
+        ss[1:n + 1].zero_()
+        eng.score(scores=big[1:n + 1], rowbest=rb[1:n + 1], selfsc=ss[1:n + 1])
+        torch.cuda.synchronize()
+        for t in (big, rb, ss):
+            assert (t[0] == SENT).all() and (t[-1] == SENT).all()
+        cm = oracle.MODE_LOCAL if mode == "local" else oracle.MODE_GLOBAL
+        assert (big[1:n + 1].cpu().numpy() == oracle.all_pairs(seqs, mode=cm)).all()
