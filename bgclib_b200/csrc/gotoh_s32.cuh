@@ -14,7 +14,7 @@
 
 namespace bgca {
 
-constexpr int K32 = 8;
+constexpr int K32 = 16;
 constexpr int PASS32 = 32 * K32;
 constexpr int NEG32 = -(1 << 28);
 
