@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
+#include <memory>
 #include <numeric>
 #include <queue>
 #include <string>
@@ -344,7 +346,7 @@ int bgca_version(void) { return BGCA_VERSION; }
 const char *bgca_last_error(void) { return g_last_error.c_str(); }
 
 int bgca_create(int device, bgca_engine **out)
-{
+try {
     if (!out) return fail(BGCA_ERR_INVALID, "bgca_create: out is NULL");
     *out = nullptr;
     int count = 0;
@@ -358,7 +360,8 @@ int bgca_create(int device, bgca_engine **out)
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10)
         return fail(BGCA_ERR_CUDA, "bgca_create: device is not sm_100 (B200) class");
-    bgca_engine *E = new bgca_engine();
+    std::unique_ptr<bgca_engine, int (*)(bgca_engine *)> guard(new bgca_engine(), bgca_destroy);
+    bgca_engine *E = guard.get();
     E->device = device;
     E->n_sm = prop.multiProcessorCount;
     CUDA_TRY(cudaEventCreate(&E->ev0));
@@ -370,8 +373,10 @@ int bgca_create(int device, bgca_engine **out)
         CUDA_TRY(cudaStreamCreateWithFlags(&E->side[i], cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&E->ev_join[i], cudaEventDisableTiming));
     }
-    *out = E;
+    *out = guard.release();
     return BGCA_OK;
+} catch (const std::exception &ex) {   // std::bad_alloc and friends must not cross the C ABI
+    return fail(BGCA_ERR_RANGE, std::string("bgca_create: ") + ex.what());
 }
 
 int bgca_destroy(bgca_engine *e)
@@ -420,7 +425,7 @@ int bgca_set_scoring(bgca_engine *e, const int8_t *sub, int32_t open, int32_t ex
 int bgca_pack(bgca_engine *e, const uint8_t *ascii, const int64_t *offsets, int32_t n,
               const int32_t *type_of_seq, const int32_t *bgc_of_seq, int32_t n_bgc,
               int32_t n_query, int32_t ascii_on_device, void *stream)
-{
+try {
     if (!e || !ascii || !offsets) return fail(BGCA_ERR_INVALID, "bgca_pack: NULL argument");
     if (n <= 0) return fail(BGCA_ERR_INVALID, "bgca_pack: need at least one sequence");
     if (bgc_of_seq && (n_bgc <= 0 || n_bgc > 65535))
@@ -537,13 +542,15 @@ int bgca_pack(bgca_engine *e, const uint8_t *ascii, const int64_t *offsets, int3
     }
     e->packed = true;
     return BGCA_OK;
+} catch (const std::exception &ex) {   // std::bad_alloc and friends must not cross the C ABI
+    return fail(BGCA_ERR_RANGE, std::string("bgca_pack: ") + ex.what());
 }
 
 int64_t bgca_packed_bytes(const bgca_engine *e) { return (e && e->packed) ? e->packed_bytes : 0; }
 
 int bgca_get_packed(const bgca_engine *e, uint8_t *codes_out, int64_t *offsets_sorted_out,
                     int32_t *order_out, void *stream)
-{
+try {
     if (!e || !e->packed) return fail(BGCA_ERR_INVALID, "bgca_get_packed: nothing packed");
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(e->device));
@@ -557,13 +564,15 @@ int bgca_get_packed(const bgca_engine *e, uint8_t *codes_out, int64_t *offsets_s
     }
     if (order_out) std::memcpy(order_out, e->order.data(), sizeof(int32_t) * e->n);
     return BGCA_OK;
+} catch (const std::exception &ex) {   // std::bad_alloc and friends must not cross the C ABI
+    return fail(BGCA_ERR_RANGE, std::string("bgca_get_packed: ") + ex.what());
 }
 
 int bgca_plan_host(const int32_t *len_sorted, const int32_t *type_sorted, const int32_t *role_sorted,
                    int32_t n, int32_t same_type_only, int32_t cross_only, int32_t mode,
                    int32_t max_abs_sub, int32_t open, int32_t extend, int32_t rank, int32_t world,
                    bgca_tile *tiles_out, int64_t capacity, int64_t *n_tiles_out, bgca_plan_info *info)
-{
+try {
     if (!len_sorted || n <= 0 || world <= 0 || rank < 0 || rank >= world)
         return fail(BGCA_ERR_INVALID, "bgca_plan_host: bad arguments");
     if (cross_only && !role_sorted) return fail(BGCA_ERR_INVALID, "bgca_plan_host: cross_only needs roles");
@@ -578,11 +587,13 @@ int bgca_plan_host(const int32_t *len_sorted, const int32_t *type_sorted, const 
         std::memcpy(tiles_out, R.tiles.data(), sizeof(bgca_tile) * (size_t)m);
     }
     return BGCA_OK;
+} catch (const std::exception &ex) {   // std::bad_alloc and friends must not cross the C ABI
+    return fail(BGCA_ERR_RANGE, std::string("bgca_plan_host: ") + ex.what());
 }
 
 int bgca_plan(bgca_engine *e, int32_t same_type_only, int32_t cross_only, int32_t rank, int32_t world,
               bgca_plan_info *info)
-{
+try {
     if (!e || !e->packed) return fail(BGCA_ERR_INVALID, "bgca_plan: call bgca_pack first");
     if (!e->scoring_set) return fail(BGCA_ERR_INVALID, "bgca_plan: call bgca_set_scoring first");
     if (world <= 0 || rank < 0 || rank >= world) return fail(BGCA_ERR_INVALID, "bgca_plan: bad rank/world");
@@ -607,6 +618,8 @@ int bgca_plan(bgca_engine *e, int32_t same_type_only, int32_t cross_only, int32_
     e->planned = true;
     if (info) *info = e->plan_info;
     return BGCA_OK;
+} catch (const std::exception &ex) {   // std::bad_alloc and friends must not cross the C ABI
+    return fail(BGCA_ERR_RANGE, std::string("bgca_plan: ") + ex.what());
 }
 
 static void fill_params(const bgca_engine *e, ScoreParams &p, int32_t *scores, int32_t *rowbest,
@@ -651,7 +664,7 @@ static int run_s32_pairs(bgca_engine *e, ScoreParams &p, const int32_t *d_pq, co
 
 int bgca_score(bgca_engine *e, int32_t *scores, int32_t *rowbest, int32_t *selfsc, int32_t type_check,
                void *stream)
-{
+try {
     if (!e || !e->planned) return fail(BGCA_ERR_INVALID, "bgca_score: call bgca_plan first");
     if (rowbest && !e->has_bgc) return fail(BGCA_ERR_INVALID, "bgca_score: rowbest needs bgc_of_seq at pack time");
     if (rowbest && type_check && !e->has_type)
@@ -742,6 +755,8 @@ int bgca_score(bgca_engine *e, int32_t *scores, int32_t *rowbest, int32_t *selfs
     CUDA_TRY(cudaEventRecord(e->ev1, st));
     e->timed = true;
     return BGCA_OK;
+} catch (const std::exception &ex) {   // std::bad_alloc and friends must not cross the C ABI
+    return fail(BGCA_ERR_RANGE, std::string("bgca_score: ") + ex.what());
 }
 
 // ORIGINAL-space device pair lists -> SORTED-space lists in e->d_pq / e->d_ps (lists are small
@@ -775,7 +790,7 @@ static int stage_pair_list(bgca_engine *e, const int32_t *pi, const int32_t *pj,
 
 int bgca_score_pairs32(bgca_engine *e, const int32_t *pi, const int32_t *pj, int64_t npairs,
                        int32_t *out, void *stream)
-{
+try {
     if (!e || !e->packed || !e->scoring_set) return fail(BGCA_ERR_INVALID, "bgca_score_pairs32: pack and set scoring first");
     if (!pi || !pj || !out || npairs < 0) return fail(BGCA_ERR_INVALID, "bgca_score_pairs32: bad arguments");
     if (npairs == 0) return BGCA_OK;
@@ -787,11 +802,13 @@ int bgca_score_pairs32(bgca_engine *e, const int32_t *pi, const int32_t *pj, int
     fill_params(e, p, nullptr, nullptr, nullptr, 0);
     e->last_launches = 0;
     return run_s32_pairs(e, p, e->d_pq.p, e->d_ps.p, npairs, out, st);
+} catch (const std::exception &ex) {   // std::bad_alloc and friends must not cross the C ABI
+    return fail(BGCA_ERR_RANGE, std::string("bgca_score_pairs32: ") + ex.what());
 }
 
 int bgca_pair_stats(bgca_engine *e, const int32_t *pi, const int32_t *pj, int64_t npairs,
                     bgca_alnstats *out, void *stream)
-{
+try {
     if (!e || !e->packed || !e->scoring_set) return fail(BGCA_ERR_INVALID, "bgca_pair_stats: pack and set scoring first");
     if (!pi || !pj || !out || npairs < 0) return fail(BGCA_ERR_INVALID, "bgca_pair_stats: bad arguments");
     if (npairs == 0) return BGCA_OK;
@@ -815,6 +832,8 @@ int bgca_pair_stats(bgca_engine *e, const int32_t *pi, const int32_t *pj, int64_
     CUDA_TRY(launch_stats(e->mode, compact, p, e->d_pq.p, e->d_ps.p, npairs, e->d_scratch_st.p, stride, out, grid, st));
     e->last_launches = 1;
     return BGCA_OK;
+} catch (const std::exception &ex) {   // std::bad_alloc and friends must not cross the C ABI
+    return fail(BGCA_ERR_RANGE, std::string("bgca_pair_stats: ") + ex.what());
 }
 
 int bgca_reduce_bgc(bgca_engine *e, const int32_t *rowbest, const int32_t *selfsc, int64_t *best,
@@ -830,7 +849,7 @@ int bgca_reduce_bgc(bgca_engine *e, const int32_t *rowbest, const int32_t *selfs
 
 int bgca_score_all_host(bgca_engine *e, const uint8_t *ascii, const int64_t *offsets, int32_t n,
                         int32_t *scores_host)
-{
+try {
     if (!e || !scores_host) return fail(BGCA_ERR_INVALID, "bgca_score_all_host: NULL argument");
     int rc = bgca_pack(e, ascii, offsets, n, nullptr, nullptr, 0, 0, 0, nullptr);
     if (rc != BGCA_OK) return rc;
@@ -849,6 +868,8 @@ int bgca_score_all_host(bgca_engine *e, const uint8_t *ascii, const int64_t *off
     if (rc != BGCA_OK) return rc;
     if (err != cudaSuccess) return fail(BGCA_ERR_CUDA, std::string("bgca_score_all_host: ") + cudaGetErrorString(err));
     return BGCA_OK;
+} catch (const std::exception &ex) {   // std::bad_alloc and friends must not cross the C ABI
+    return fail(BGCA_ERR_RANGE, std::string("bgca_score_all_host: ") + ex.what());
 }
 
 int bgca_last_launches(const bgca_engine *e) { return e ? e->last_launches : 0; }
