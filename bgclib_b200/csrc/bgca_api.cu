@@ -41,7 +41,6 @@ const VariantDesc kVariants[] = {
 #undef X
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
-constexpr int kMaxPackedRows = 32 * 32;   // largest G*K
 constexpr int kSubjectsPerGroup = 16;
 constexpr uint64_t kPackedHeader = 64;    // bytes of TOK_IDLE (25) in front of the first sequence
 
@@ -68,10 +67,9 @@ int pick_variant(int Lq, int mode, int n_subjects = 1 << 30)
     double best_cost = 0.0;
     const int force_g = forced_group_width();
     (void)mode;   // local and global kernels have the same register budget
-    const int k_cap = 32;
     for (int v = 0; v < kNumVariants; ++v) {
         const int G = kVariants[v].G, K = kVariants[v].K;
-        if (G * K < Lq || K > k_cap) continue;
+        if (G * K < Lq) continue;
         if (G == 4 && force_g != 4 && n_subjects < 4 * (CTA_THREADS / 4)) continue;
         if (force_g && G != force_g && force_g * 32 >= Lq) continue;
         const double c = variant_cost(G, K, Lq);

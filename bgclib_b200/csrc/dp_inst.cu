@@ -44,6 +44,9 @@ cudaError_t BGCA_CAT(launch_pair16_g, BGCA_INST_G, _m, BGCA_INST_MODE, _p, BGCA_
     case KK:     \
         return launch_one<BGCA_INST_G, KK, BGCA_INST_MODE, BGCA_INST_PRESET>(p, n_sm, st, grid_out);
         BGCA_K_LIST(X, BGCA_INST_G)
+#if BGCA_INST_G == 32
+        BGCA_K_LIST_WIDE(X, BGCA_INST_G)
+#endif
 #undef X
         default:
             return cudaErrorInvalidValue;

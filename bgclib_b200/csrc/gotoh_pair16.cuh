@@ -79,8 +79,8 @@ struct Pair16Cfg {
     static constexpr int BEST_BYTES = NGROUPS * 32 * 2 * 4;   // per group: ring of 32 (lo, hi) slots
     static constexpr int SMEM_BYTES = PROF_BYTES + BEST_BYTES + 2 * LPAD + NSYM * NSYM + 16;
     // registers: 2K state + 4CH profile + ~24 -> pick CTAs/SM so ptxas has room.
-    static constexpr int MIN_CTAS_LOCAL = (K <= 6) ? 5 : (K <= 14) ? 4 : (K <= 18) ? 3 : 2;
-    static constexpr int MIN_CTAS_GLOBAL = (K <= 4) ? 5 : (K <= 9) ? 4 : (K <= 14) ? 3 : 2;   // a few more live values (boundary walk)
+    static constexpr int MIN_CTAS_LOCAL = (K <= 6) ? 5 : (K <= 14) ? 4 : (K <= 18) ? 3 : (K <= 32) ? 2 : 1;
+    static constexpr int MIN_CTAS_GLOBAL = (K <= 4) ? 5 : (K <= 9) ? 4 : (K <= 14) ? 3 : (K <= 32) ? 2 : 1;   // a few more live values (boundary walk)
 };
 
 // Gap presets: with the gap scores known at compile time the DPX ops take them as

@@ -94,6 +94,18 @@ def test_long_sequences_take_the_32bit_kernel():
     assert loc[6, 6] == 35200
 
 
+@pytest.mark.parametrize("mode", ["local", "global"])
+def test_protein_length_queries_stay_on_the_packed_kernel(mode):
+    """Queries of 1025..2048 residues run in ONE pass of the whole-warp variants with 40..64
+    rows per lane (no 32-bit fallback)."""
+    rng = np.random.default_rng(17 + (mode == "global"))
+    seqs = _related(rng, 2, 4, 1025, 2048) + [_rand(rng, k) for k in (1025, 1280, 1281, 1536, 1793, 2047, 2048, 90)]
+    res = domain_pair_scores(seqs, mode=mode)
+    assert res.plan["n_fallback32"] == 0
+    cm = oracle.MODE_LOCAL if mode == "local" else oracle.MODE_GLOBAL
+    assert (res.scores == oracle.all_pairs(seqs, mode=cm)).all()
+
+
 def test_pair_list_32bit_kernel():
     rng = np.random.default_rng(6)
     seqs = _related(rng, 3, 4, 100, 700)
