@@ -4,7 +4,7 @@ similarity.  Hand-written sm_100a CUDA behind a C ABI (include/bgca.h);
 PyTorch only carries device memory, streams and torch.distributed.
 """
 from .alphabet import ALPHABET, BLOSUM62  # noqa: F401
-from .api import (BGCSimilarity, DomainPairScores, DomainPairStats, attach, bgc_similarity,  # noqa: F401
+from .api import (BGCSimilarity, DomainPairScores, DomainPairStats, PackedDatabase, attach, bgc_similarity,  # noqa: F401
                   domain_pair_scores, domain_pair_stats, get_engine)
 from .engine import Engine, dpx_probe, load_library, plan_host  # noqa: F401
 from .extract import DomainBatch, DomainRecord, extract  # noqa: F401

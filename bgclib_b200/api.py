@@ -126,12 +126,25 @@ def domain_pair_scores(source, *, database=None, mode="local", matrix="BLOSUM62"
     n = len(batch)
     if n == 0:
         raise ValueError("no domain sequences selected")
-    eng = get_engine(device)
+    pdb = database if isinstance(database, PackedDatabase) else None
+    eng = pdb.engine if pdb is not None else get_engine(device)
     eng.set_scoring(matrix, open_gap_score, extend_gap_score, mode)
     torch = eng.torch
     dist, rank, world = _dist()
     db = None
-    if database is not None:
+    if pdb is not None:
+        # persistent database: only the queries are uploaded and encoded; [database | queries]
+        db = pdb.batch
+        pos = dict(pdb.type_pos)
+        for t in batch.type_names:
+            pos.setdefault(t, len(pos))
+        q_types = np.asarray([pos[t] for t in batch.type_names], dtype=np.int32)[batch.type_of_seq]
+        Bd = len(db.bgc_ids)
+        eng.pack_append(batch.sequences, type_of_seq=q_types, bgc_of_seq=batch.bgc_of_seq + Bd,
+                        n_bgc_total=Bd + max(1, len(batch.bgc_ids)))
+        plan = eng.plan(same_type_only=same_type_only, rank=rank, world=world, cross_only=2)
+        ncols = len(db)
+    elif database is not None:
         db = _as_batch(database, unit, cbp_only, alias, domain_types)
         if len(db) == 0:
             raise ValueError("no domain sequences selected in the database")
@@ -193,6 +206,12 @@ def bgc_similarity(source, *, database=None, matrix="BLOSUM62", open_gap_score=-
     ``attempted_domain_prediction`` flag (BGCtoolkit.py:552-560).
     """
     batch = _as_batch(source, unit, cbp_only, alias, domain_types)
+    if isinstance(database, PackedDatabase):
+        from .alphabet import resolve_matrix
+        if (int(open_gap_score), int(extend_gap_score)) != database.scoring[1:] or \
+                not np.array_equal(resolve_matrix(matrix), resolve_matrix(database.scoring[0])):
+            raise ValueError("scoring parameters differ from the ones the PackedDatabase was built with")
+        return _bgc_similarity_persistent(batch, database, same_type_only, return_device)
     if database is not None:
         return _bgc_similarity_cross(batch, _as_batch(database, unit, cbp_only, alias, domain_types),
                                      matrix, open_gap_score, extend_gap_score, same_type_only, device,
@@ -317,6 +336,75 @@ def _bgc_similarity_cross(q: DomainBatch, d: DomainBatch, matrix, open_gap_score
         sim_x, best_qd, best_dq, selfsum = (x.cpu().numpy() for x in (sim_x, best_qd, best_dq, selfsum))
     return BGCSimilarity(sim_x, best_qd, selfsum[:Bq], list(q.bgc_ids), q.records + d.records, plan,
                          list(d.bgc_ids), selfsum[Bq:], best_dq)
+
+
+class PackedDatabase:
+    """A collection packed once and kept in HBM ("a precomputed database", BGClib/Readme.md:18):
+
+        db = bgclib_b200.PackedDatabase(mibig_collection, alias=hmmdb.alias)
+        hits = bgclib_b200.bgc_similarity(new_collection, database=db, alias=hmmdb.alias)
+
+    It owns its own engine (the packed residues, the type/BGC tables and the self score of every
+    database domain stay on the device); every query call only uploads and encodes the query
+    sequences behind it (bgca_pack_append) and aligns query x database pairs.  Scoring parameters
+    are fixed at construction — the cached self scores depend on them."""
+
+    def __init__(self, source, *, matrix="BLOSUM62", open_gap_score=-12, extend_gap_score=-1, unit="domain",
+                 cbp_only=True, alias=None, domain_types=None, device=None):
+        import torch
+        self.batch = _as_batch(source, unit, cbp_only, alias, domain_types)
+        if len(self.batch) == 0 or len(self.batch.bgc_ids) == 0:
+            raise ValueError("the database holds no domain sequences")
+        if device is None:
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        self.engine = Engine(int(device))
+        self.scoring = (matrix, int(open_gap_score), int(extend_gap_score))
+        eng = self.engine
+        eng.set_scoring(matrix, open_gap_score, extend_gap_score, "local")
+        eng.pack(self.batch.sequences, type_of_seq=self.batch.type_of_seq, bgc_of_seq=self.batch.bgc_of_seq,
+                 n_bgc=len(self.batch.bgc_ids))
+        # self scores of the database domains, once (the similarity is normalised with them)
+        idx = torch.arange(len(self.batch), dtype=torch.int32, device=eng.tdev)
+        self.selfsc = eng.score_pairs32(idx, idx)
+        self.type_pos = {t: i for i, t in enumerate(self.batch.type_names)}
+
+    def __len__(self):
+        return len(self.batch)
+
+
+def _bgc_similarity_persistent(q: DomainBatch, db: PackedDatabase, same_type_only, return_device) -> BGCSimilarity:
+    d = db.batch
+    Bq, Bd, nd, nq = len(q.bgc_ids), len(d.bgc_ids), len(d), len(q)
+    if Bq == 0 or nq == 0:
+        raise ValueError("the query holds no BGCs with domain sequences")
+    eng = db.engine
+    torch = eng.torch
+    # query type ids in the database's type-id space (types the database lacks get fresh ids)
+    pos = dict(db.type_pos)
+    for t in q.type_names:
+        pos.setdefault(t, len(pos))
+    q_types = np.asarray([pos[t] for t in q.type_names], dtype=np.int32)[q.type_of_seq]
+    dist, rank, world = _dist()
+    eng.set_scoring(*db.scoring, "local")
+    # index spaces on this path: [database | queries], BGCs likewise
+    eng.pack_append(q.sequences, type_of_seq=q_types, bgc_of_seq=q.bgc_of_seq + Bd, n_bgc_total=Bd + Bq)
+    plan = eng.plan(same_type_only=same_type_only, rank=rank, world=world, cross_only=2)
+    n, B = nd + nq, Bd + Bq
+    rowbest = torch.zeros((n, B), dtype=torch.int32, device=eng.tdev)
+    selfsc = torch.zeros((n,), dtype=torch.int32, device=eng.tdev)
+    eng.score(rowbest=rowbest, selfsc=selfsc, type_check=False)
+    if dist is not None:
+        dist.all_reduce(rowbest, op=dist.ReduceOp.MAX)
+        dist.all_reduce(selfsc, op=dist.ReduceOp.MAX)
+    selfsc[:nd] = db.selfsc
+    sim, best, selfsum = eng.reduce_bgc(rowbest, selfsc)
+    sim_x = sim[Bd:, :Bd].contiguous()
+    best_qd = best[Bd:, :Bd].contiguous()
+    best_dq = best[:Bd, Bd:].contiguous()
+    if not return_device:
+        sim_x, best_qd, best_dq, selfsum = (x.cpu().numpy() for x in (sim_x, best_qd, best_dq, selfsum))
+    return BGCSimilarity(sim_x, best_qd, selfsum[Bd:], list(q.bgc_ids), q.records + d.records, plan,
+                         list(d.bgc_ids), selfsum[:Bd], best_dq)
 
 
 @dataclass

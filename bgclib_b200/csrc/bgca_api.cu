@@ -115,9 +115,12 @@ struct PlanResult {
 // role (nullable): 0 = query, 1 = database; sorted as (type, role, length).  cross_only: only
 // query x database pairs are planned, plus one self-only tile per sequence pair (reserved = 1)
 // so that the self scores the similarity is normalised with exist.
+// n_db_first > 0 (cross plans only): sorted [0, n_db_first) is a persistent database sorted by
+// (type, length) and [n_db_first, n) the appended queries, sorted the same way; cross_only == 2
+// then leaves out the database's self tiles (its self scores are cached by the caller).
 PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *role, int32_t n,
-                     int same_type_only, int cross_only, int mode, int max_abs_sub, int open, int extend,
-                     int rank, int world)
+                     int same_type_only, int cross_only, int32_t n_db_first, int mode, int max_abs_sub,
+                     int open, int extend, int rank, int world)
 {
     PlanResult R;
     std::vector<int64_t> pre(n + 1, 0);
@@ -176,7 +179,75 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
     };
     if (!small_plan) R.tiles.reserve(((size_t)n * ((size_t)n / (2 * 128 * (size_t)spg) + 2) / 2) / (size_t)world + 64);
 
+    auto self_tile = [&](int qa, int qb) {
+        const int La = len[qa], Lb = (qb >= 0) ? len[qb] : 0;
+        const int Lq = std::max(La, Lb);
+        bgca_tile T{};
+        T.qa = qa; T.qb = qb; T.s_begin = qa; T.s_end = (qb >= 0 ? qb : qa) + 1;
+        T.variant = pick_variant(Lq, mode, 1);
+        T.reserved = 1;
+        if (T.variant && !fits_int16(mode, max_abs_sub, open, extend, Lq, Lq)) T.variant = 0;
+        T.cells = (int64_t)(La + Lb) * (pre[T.s_end] - pre[T.s_begin]);
+        produce(T);
+    };
+    // query pair (qa, qb) against the subjects [sub0, te), cut into chunks
+    auto row_tiles = [&](int qa, int qb, int sub0, int te) {
+        const int La = len[qa], Lb = (qb >= 0) ? len[qb] : 0;
+        const int Lq = std::max(La, Lb);
+        const int S = te - sub0;
+        if (S <= 0) return;
+        const int variant = pick_variant(Lq, mode, S);
+        const int G = variant >> 8;
+        // subjects per tile: ~spg per alignment group (= subject stream) of the CTA,
+        // split evenly over the row and rounded up to a whole number per group
+        const int ngroups = variant ? CTA_THREADS / G : 16;
+        const int s_max = ngroups * spg;
+        const int nchunks = (S + s_max - 1) / s_max;
+        int chunk = (S + nchunks - 1) / nchunks;
+        chunk = (chunk + ngroups - 1) / ngroups * ngroups;
+        for (int s0 = sub0; s0 < te; s0 += chunk) {
+            const int s1 = std::min(te, s0 + chunk);
+            bgca_tile T{};
+            T.qa = qa; T.qb = qb; T.s_begin = s0; T.s_end = s1;
+            T.variant = variant;
+            if (variant && !fits_int16(mode, max_abs_sub, open, extend, Lq, len[s1 - 1])) T.variant = 0;
+            T.cells = (int64_t)(La + Lb) * (pre[s1] - pre[s0]);
+            produce(T);
+        }
+    };
+
     int tb = 0;
+    if (cross_only && n_db_first > 0) {
+        // persistent database in front, queries behind: every query type block meets the
+        // database's run of the same type (or the whole database)
+        const int nd = n_db_first;
+        for (int q0 = nd; q0 < n;) {
+            int q1 = n, d0 = 0, d1 = nd;
+            if (same_type_only && type) {
+                q1 = q0 + 1;
+                while (q1 < n && type[q1] == type[q0]) ++q1;
+                d0 = (int)(std::lower_bound(type, type + nd, type[q0]) - type);
+                d1 = (int)(std::upper_bound(type, type + nd, type[q0]) - type);
+            }
+            for (int qa = q0; qa < q1; qa += 2) {
+                const int qb = (qa + 1 < q1) ? qa + 1 : -1;
+                row_tiles(qa, qb, d0, d1);
+                self_tile(qa, qb);
+            }
+            q0 = q1;
+        }
+        if (cross_only == 1)                 // the database's own self scores too
+            for (int d = 0; d < nd;) {
+                int de = nd;
+                if (same_type_only && type) {
+                    de = d + 1;
+                    while (de < nd && type[de] == type[d]) ++de;
+                }
+                for (int qa = d; qa < de; qa += 2) self_tile(qa, (qa + 1 < de) ? qa + 1 : -1);
+                d = de;
+            }
+        tb = n;                              // the generic loop below has nothing left to do
+    }
     while (tb < n) {
         int te = n;
         if (same_type_only && type) {
@@ -191,46 +262,13 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
         }
         for (int qa = tb; qa < tm; qa += 2) {
             const int qb = (qa + 1 < tm) ? qa + 1 : -1;
-            const int La = len[qa], Lb = (qb >= 0) ? len[qb] : 0;
-            const int Lq = std::max(La, Lb);
-            const int sub0 = cross_only ? tm : qa;
-            const int S = te - sub0;
-            if (S <= 0) continue;
-            int variant = pick_variant(Lq, mode, S);
-            const int G = variant >> 8;
-            // subjects per tile: ~spg per alignment group (= subject stream) of the CTA,
-            // split evenly over the row and rounded up to a whole number per group
-            const int ngroups = variant ? CTA_THREADS / G : 16;
-            const int s_max = ngroups * spg;
-            const int nchunks = (S + s_max - 1) / s_max;
-            int chunk = (S + nchunks - 1) / nchunks;
-            chunk = (chunk + ngroups - 1) / ngroups * ngroups;
-            for (int s0 = sub0; s0 < te; s0 += chunk) {
-                const int s1 = std::min(te, s0 + chunk);
-                bgca_tile T{};
-                T.qa = qa; T.qb = qb; T.s_begin = s0; T.s_end = s1;
-                T.variant = variant;
-                if (variant && !fits_int16(mode, max_abs_sub, open, extend, Lq, len[s1 - 1])) T.variant = 0;
-                T.cells = (int64_t)(La + Lb) * (pre[s1] - pre[s0]);
-                produce(T);
-            }
+            row_tiles(qa, qb, cross_only ? tm : qa, te);
         }
         if (cross_only) {
             // self-only tiles for every sequence of the block (queries and database alike)
             for (int r0 = tb; r0 < te;) {
                 const int r_end = (r0 < tm) ? tm : te;          // pairs never straddle the role boundary
-                for (int qa = r0; qa < r_end; qa += 2) {
-                    const int qb = (qa + 1 < r_end) ? qa + 1 : -1;
-                    const int La = len[qa], Lb = (qb >= 0) ? len[qb] : 0;
-                    const int Lq = std::max(La, Lb);
-                    bgca_tile T{};
-                    T.qa = qa; T.qb = qb; T.s_begin = qa; T.s_end = (qb >= 0 ? qb : qa) + 1;
-                    T.variant = pick_variant(Lq, mode, 1);
-                    T.reserved = 1;
-                    if (T.variant && !fits_int16(mode, max_abs_sub, open, extend, Lq, Lq)) T.variant = 0;
-                    T.cells = (int64_t)(La + Lb) * (pre[T.s_end] - pre[T.s_begin]);
-                    produce(T);
-                }
+                for (int qa = r0; qa < r_end; qa += 2) self_tile(qa, (qa + 1 < r_end) ? qa + 1 : -1);
                 r0 = r_end;
             }
         }
@@ -284,6 +322,24 @@ struct DevBuf {
         if (e == cudaSuccess) cap = count;
         return e;
     }
+    // grow to `count` elements, keeping the first `keep` (device-to-device copy on `st`)
+    cudaError_t grow_keep(size_t count, size_t keep, cudaStream_t st)
+    {
+        if (count <= cap && p) return cudaSuccess;
+        T *np_ = nullptr;
+        const size_t want = count + count / 4;          // headroom: query sets vary from call to call
+        cudaError_t e = cudaMalloc(&np_, std::max<size_t>(want, 1) * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (p && keep) {
+            e = cudaMemcpyAsync(np_, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { cudaFree(np_); return e; }
+        }
+        if (p) cudaFree(p);
+        p = np_;
+        cap = want;
+        return cudaSuccess;
+    }
     void release()
     {
         if (p) cudaFree(p);
@@ -304,7 +360,11 @@ struct bgca_engine {
     // packed batch (host mirrors, SORTED space unless named *_orig)
     int32_t n = 0, n_bgc = 0;
     std::vector<int32_t> len, type, bgc, role, order, inv_order;
-    int32_t n_query = 0;          // sequences with role 0 (they come first in ORIGINAL order)
+    int32_t n_query = 0;          // sequences with role 0
+    // persistent database: sequences [0, n_db) of BOTH index spaces are a database that stays
+    // packed while query sets are appended behind it (bgca_pack_append); 0 = none
+    int32_t n_db = 0;
+    uint64_t db_bytes = 0;        // packed bytes of the database part
     bool has_role = false, cross_planned = false;
     std::vector<uint32_t> seq_off;
     std::vector<int32_t> bgc_start, bgc_doms;   // CSR over ORIGINAL indices
@@ -433,6 +493,7 @@ try {
     CUDA_TRY(cudaSetDevice(e->device));
     e->packed = false;
     e->planned = false;
+    e->n_db = 0;
 
     std::vector<int32_t> len_orig(n);
     for (int i = 0; i < n; ++i) {
@@ -544,6 +605,138 @@ try {
     return fail(BGCA_ERR_RANGE, std::string("bgca_pack: ") + ex.what());
 }
 
+int bgca_pack_append(bgca_engine *e, const uint8_t *ascii, const int64_t *offsets, int32_t n_new,
+                     const int32_t *type_of_seq, const int32_t *bgc_of_seq, int32_t n_bgc_total,
+                     int32_t ascii_on_device, void *stream)
+try {
+    if (!e || !ascii || !offsets) return fail(BGCA_ERR_INVALID, "bgca_pack_append: NULL argument");
+    if (!e->packed) return fail(BGCA_ERR_INVALID, "bgca_pack_append: pack the database first (bgca_pack, n_query = 0)");
+    if (e->n_db == 0 && e->n_query != 0)
+        return fail(BGCA_ERR_INVALID, "bgca_pack_append: the packed batch already holds queries (n_query != 0)");
+    if (n_new <= 0) return fail(BGCA_ERR_INVALID, "bgca_pack_append: need at least one query sequence");
+    if ((type_of_seq != nullptr) != e->has_type || (bgc_of_seq != nullptr) != e->has_bgc)
+        return fail(BGCA_ERR_INVALID, "bgca_pack_append: give type_of_seq / bgc_of_seq exactly as for the database");
+    if (bgc_of_seq && (n_bgc_total <= 0 || n_bgc_total > 65535))
+        return fail(BGCA_ERR_RANGE, "bgca_pack_append: n_bgc_total must be in 1..65535");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(e->device));
+    if (e->n_db == 0) {                      // first query set: everything packed so far is the database
+        e->n_db = e->n;
+        e->db_bytes = (uint64_t)e->packed_bytes;
+    }
+    const int n_db = e->n_db;
+    if ((int64_t)n_db + n_new > 0x7FFFFFF0) return fail(BGCA_ERR_RANGE, "bgca_pack_append: too many sequences");
+    e->packed = false;
+    e->planned = false;
+
+    std::vector<int32_t> len_new(n_new);
+    for (int i = 0; i < n_new; ++i) {
+        const int64_t l = offsets[i + 1] - offsets[i];
+        if (l < 0) return fail(BGCA_ERR_INVALID, "bgca_pack_append: offsets must be non-decreasing");
+        if (l == 0) return fail(BGCA_ERR_EMPTY, "sequence " + std::to_string(i) + " has zero length");
+        if (l > 65535) return fail(BGCA_ERR_RANGE, "sequence " + std::to_string(i) + " longer than 65535");
+        len_new[i] = (int32_t)l;
+    }
+    if (bgc_of_seq)
+        for (int i = 0; i < n_new; ++i)
+            if (bgc_of_seq[i] < 0 || bgc_of_seq[i] >= n_bgc_total)
+                return fail(BGCA_ERR_INVALID, "bgca_pack_append: bgc_of_seq out of range");
+
+    // queries sorted by (type, length) among themselves, placed behind the database in BOTH
+    // index spaces: sorted r = n_db + k  <->  original n_db + (position in the query list)
+    std::vector<int> qord(n_new);
+    std::iota(qord.begin(), qord.end(), 0);
+    std::stable_sort(qord.begin(), qord.end(), [&](int a, int b) {
+        const int ta = type_of_seq ? type_of_seq[a] : 0, tb = type_of_seq ? type_of_seq[b] : 0;
+        if (ta != tb) return ta < tb;
+        return len_new[a] < len_new[b];
+    });
+    const int n = n_db + n_new;
+    e->len.resize(n); e->type.resize(n); e->bgc.resize(n); e->role.resize(n); e->seq_off.resize(n);
+    e->order.resize(n); e->inv_order.resize(n);
+    for (int r = 0; r < n_db; ++r) e->role[r] = 1;
+    uint64_t off = e->db_bytes;
+    for (int k = 0; k < n_new; ++k) {
+        const int r = n_db + k, o = qord[k];
+        e->order[r] = n_db + o;
+        e->inv_order[n_db + o] = r;
+        e->len[r] = len_new[o];
+        e->type[r] = type_of_seq ? type_of_seq[o] : 0;
+        e->bgc[r] = bgc_of_seq ? bgc_of_seq[o] : 0;
+        e->role[r] = 0;
+        e->seq_off[r] = (uint32_t)off;
+        off += (uint64_t)((len_new[o] + 1 + 15) & ~15);
+        if (off > 0xFFFFFFF0ull) return fail(BGCA_ERR_RANGE, "bgca_pack_append: packed batch exceeds 4 GiB");
+    }
+    e->n = n;
+    e->n_query = n_new;
+    e->has_role = true;
+    e->cross_planned = false;
+    e->packed_bytes = (int64_t)off;
+    if (bgc_of_seq) {
+        e->n_bgc = n_bgc_total;
+        e->bgc_start.assign((size_t)e->n_bgc + 1, 0);
+        e->bgc_doms.assign(n, 0);
+        for (int r = 0; r < n; ++r) e->bgc_start[e->bgc[r] + 1]++;
+        for (int b = 0; b < e->n_bgc; ++b) e->bgc_start[b + 1] += e->bgc_start[b];
+        std::vector<int32_t> cur(e->bgc_start.begin(), e->bgc_start.end() - 1);
+        std::vector<int32_t> bgc_orig(n);
+        for (int r = 0; r < n; ++r) bgc_orig[e->order[r]] = e->bgc[r];
+        for (int i = 0; i < n; ++i) e->bgc_doms[cur[bgc_orig[i]]++] = i;      // ORIGINAL indices, ascending per BGC
+    }
+
+    const int64_t total_ascii = offsets[n_new] - offsets[0];
+    const uint8_t *d_src = ascii + offsets[0];
+    if (!ascii_on_device) {
+        CUDA_TRY(e->d_ascii.reserve((size_t)total_ascii + 16));
+        CUDA_TRY(cudaMemcpyAsync(e->d_ascii.p, ascii + offsets[0], (size_t)total_ascii, cudaMemcpyHostToDevice, st));
+        d_src = e->d_ascii.p;
+    }
+    std::vector<int64_t> off_rel(n_new);
+    for (int k = 0; k < n_new; ++k) off_rel[k] = offsets[qord[k]] - offsets[0];
+    CUDA_TRY(e->d_codes.grow_keep((size_t)off + 16, (size_t)e->db_bytes, st));
+    CUDA_TRY(e->d_offsets_orig.reserve(n_new));
+    CUDA_TRY(e->d_order.reserve(n));
+    CUDA_TRY(e->d_len.reserve(n));
+    CUDA_TRY(e->d_type.reserve(n));
+    CUDA_TRY(e->d_bgc.reserve(n));
+    CUDA_TRY(e->d_seq_off.reserve(n));
+    CUDA_TRY(e->d_err.reserve(1));
+    CUDA_TRY(e->d_bgc_start.reserve(e->bgc_start.size()));
+    CUDA_TRY(e->d_bgc_doms.reserve(std::max<size_t>(e->bgc_doms.size(), 1)));
+    CUDA_TRY(cudaMemcpyAsync(e->d_offsets_orig.p, off_rel.data(), sizeof(int64_t) * n_new, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->d_order.p, e->order.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->d_len.p, e->len.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->d_type.p, e->type.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->d_bgc.p, e->bgc.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->d_seq_off.p, e->seq_off.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+    if (bgc_of_seq) {
+        CUDA_TRY(cudaMemcpyAsync(e->d_bgc_start.p, e->bgc_start.data(), sizeof(int32_t) * e->bgc_start.size(), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(e->d_bgc_doms.p, e->bgc_doms.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    }
+    CUDA_TRY(cudaMemsetAsync(e->d_err.p, 0xFF, sizeof(unsigned long long), st));
+    CUDA_TRY(cudaMemsetAsync(e->d_codes.p + off, BGCA_PAD_CODE, 16, st));
+    CUDA_TRY(cudaEventRecord(e->evp0, st));
+    CUDA_TRY(launch_pack(d_src, e->d_offsets_orig.p, e->d_order.p + n_db, e->d_seq_off.p + n_db, e->d_len.p + n_db,
+                         n_new, e->d_codes.p, e->d_err.p, st));
+    CUDA_TRY(cudaEventRecord(e->evp1, st));
+    e->pack_timed = true;
+    unsigned long long err = 0;
+    CUDA_TRY(cudaMemcpyAsync(&err, e->d_err.p, sizeof(err), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (err != ~0ULL) {
+        // a failed query set leaves the database intact: the next bgca_pack_append starts over
+        e->n = n_db; e->n_query = 0; e->packed_bytes = (int64_t)e->db_bytes; e->packed = true;
+        const unsigned seq = (unsigned)(err >> 32) - (unsigned)n_db, pos = (unsigned)(err & 0xFFFFFFFFu);
+        return fail(BGCA_ERR_ALPHABET, "sequence " + std::to_string(seq) + " contains a letter not in the "
+                                       "alphabet ARNDCQEGHILKMFPSTWYVBZX* at position " + std::to_string(pos));
+    }
+    e->packed = true;
+    return BGCA_OK;
+} catch (const std::exception &ex) {
+    return fail(BGCA_ERR_RANGE, std::string("bgca_pack_append: ") + ex.what());
+}
+
 int64_t bgca_packed_bytes(const bgca_engine *e) { return (e && e->packed) ? e->packed_bytes : 0; }
 
 int bgca_get_packed(const bgca_engine *e, uint8_t *codes_out, int64_t *offsets_sorted_out,
@@ -567,17 +760,20 @@ try {
 }
 
 int bgca_plan_host(const int32_t *len_sorted, const int32_t *type_sorted, const int32_t *role_sorted,
-                   int32_t n, int32_t same_type_only, int32_t cross_only, int32_t mode,
+                   int32_t n, int32_t same_type_only, int32_t cross_only, int32_t n_db_first, int32_t mode,
                    int32_t max_abs_sub, int32_t open, int32_t extend, int32_t rank, int32_t world,
                    bgca_tile *tiles_out, int64_t capacity, int64_t *n_tiles_out, bgca_plan_info *info)
 try {
     if (!len_sorted || n <= 0 || world <= 0 || rank < 0 || rank >= world)
         return fail(BGCA_ERR_INVALID, "bgca_plan_host: bad arguments");
-    if (cross_only && !role_sorted) return fail(BGCA_ERR_INVALID, "bgca_plan_host: cross_only needs roles");
-    if (cross_only && !roles_partitioned(type_sorted, role_sorted, n, same_type_only))
+    if (n_db_first < 0 || n_db_first >= n || (n_db_first > 0 && !cross_only))
+        return fail(BGCA_ERR_INVALID, "bgca_plan_host: n_db_first needs a cross plan and 0 <= n_db_first < n");
+    if (cross_only && n_db_first == 0 && !role_sorted)
+        return fail(BGCA_ERR_INVALID, "bgca_plan_host: cross_only needs roles");
+    if (cross_only && n_db_first == 0 && !roles_partitioned(type_sorted, role_sorted, n, same_type_only))
         return fail(BGCA_ERR_INVALID, "bgca_plan_host: cross_only needs every planned block sorted queries-first");
-    PlanResult R = make_plan(len_sorted, type_sorted, role_sorted, n, same_type_only, cross_only, mode,
-                             max_abs_sub, open, extend, rank, world);
+    PlanResult R = make_plan(len_sorted, type_sorted, role_sorted, n, same_type_only, cross_only, n_db_first,
+                             mode, max_abs_sub, open, extend, rank, world);
     if (n_tiles_out) *n_tiles_out = (int64_t)R.tiles.size();
     if (info) *info = R.info;
     if (tiles_out) {
@@ -599,13 +795,17 @@ try {
         return fail(BGCA_ERR_INVALID, "bgca_plan: same_type_only needs type_of_seq at pack time");
     if (cross_only && (!e->has_role || e->n_query >= e->n))
         return fail(BGCA_ERR_INVALID, "bgca_plan: cross_only needs 0 < n_query < n at pack time");
-    if (cross_only && !roles_partitioned(e->has_type ? e->type.data() : nullptr, e->role.data(), e->n, same_type_only))
+    if (cross_only && e->n_db == 0 &&
+        !roles_partitioned(e->has_type ? e->type.data() : nullptr, e->role.data(), e->n, same_type_only))
         return fail(BGCA_ERR_INVALID, "bgca_plan: cross_only without same_type_only needs a batch packed "
                                       "without type_of_seq (the packer sorts by type before role)");
+    if (!cross_only && e->n_db > 0)
+        return fail(BGCA_ERR_INVALID, "bgca_plan: a database with appended queries takes a cross plan "
+                                      "(cross_only = 1, or 2 to leave out the database's self tiles)");
     CUDA_TRY(cudaSetDevice(e->device));
     PlanResult R = make_plan(e->len.data(), e->has_type ? e->type.data() : nullptr, e->role.data(), e->n,
-                             same_type_only, cross_only, e->mode, e->max_abs_sub, e->open, e->extend, rank,
-                             world);
+                             same_type_only, cross_only, e->n_db, e->mode, e->max_abs_sub, e->open, e->extend,
+                             rank, world);
     e->cross_planned = cross_only != 0;
     e->tiles.swap(R.tiles);
     e->plan_info = R.info;
@@ -641,6 +841,7 @@ static void fill_params(const bgca_engine *e, ScoreParams &p, int32_t *scores, i
     p.ext2 = ((uint32_t)e->extend & 0xFFFFu) * 0x10001u;
     p.type_check = type_check;
     p.cross_nq = e->cross_planned ? e->n_query : 0;
+    p.cross_q0 = e->cross_planned ? e->n_db : 0;       // queries sit behind a persistent database
     std::memcpy(p.sub, e->sub, NSYM * NSYM);
 }
 

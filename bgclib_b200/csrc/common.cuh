@@ -33,7 +33,10 @@ struct ScoreParams {
     int32_t open, extend;      // negative scores
     uint32_t open2, ext2;      // the same, replicated in both 16-bit halves
     int32_t type_check;
-    int32_t cross_nq;          // > 0: query-vs-database plan; ORIGINAL indices < cross_nq are queries
+    // query-vs-database plan (cross_nq > 0): ORIGINAL indices [cross_q0, cross_q0 + cross_nq) are the
+    // queries, the rest the database.  cross_q0 = 0 for a batch packed [queries | database] in one
+    // call, = n_database when queries were appended behind a persistent database.
+    int32_t cross_nq, cross_q0;
     int8_t sub[NSYM * NSYM];
 };
 
@@ -42,16 +45,22 @@ struct ScoreParams {
 // even though the packed halves also sweep the mirrored first pair.
 __device__ __forceinline__ void emit_pair(const ScoreParams &p, int q, int s, int32_t score)
 {
-    if (q < 0 || s < q) return;
+    if (q < 0) return;
     const int oq = p.order[q], os = p.order[s];
     if (p.cross_nq > 0) {
-        // query-vs-database: only cross pairs and self pairs count; scores is [n_query x n_db]
-        const bool q_is_query = oq < p.cross_nq, s_is_query = os < p.cross_nq;
+        // query-vs-database: only cross pairs and self pairs count (the planner lists every cross
+        // pair once, in either order); scores is [n_query x n_db]
+        const bool q_is_query = (unsigned)(oq - p.cross_q0) < (unsigned)p.cross_nq;
+        const bool s_is_query = (unsigned)(os - p.cross_q0) < (unsigned)p.cross_nq;
         if (q != s && q_is_query == s_is_query) return;
         if (p.scores && q != s) {
-            const int row = q_is_query ? oq : os, col = (q_is_query ? os : oq) - p.cross_nq;
+            const int oqq = q_is_query ? oq : os, odb = q_is_query ? os : oq;
+            const int row = oqq - p.cross_q0;
+            const int col = p.cross_q0 == 0 ? odb - p.cross_nq : odb;      // database index
             p.scores[(size_t)row * (p.n - p.cross_nq) + col] = score;
         }
+    } else if (s < q) {
+        return;
     } else if (p.scores) {
         p.scores[(size_t)oq * p.n + os] = score;
         p.scores[(size_t)os * p.n + oq] = score;

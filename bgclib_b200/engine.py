@@ -31,7 +31,7 @@ _lib = None
 # every symbol include/bgca.h declares (tests check the library exports them all)
 EXPORTED_SYMBOLS = (
     "bgca_version", "bgca_last_error", "bgca_create", "bgca_destroy", "bgca_set_scoring",
-    "bgca_pack", "bgca_packed_bytes", "bgca_get_packed", "bgca_plan", "bgca_plan_host",
+    "bgca_pack", "bgca_pack_append", "bgca_packed_bytes", "bgca_get_packed", "bgca_plan", "bgca_plan_host",
     "bgca_score", "bgca_score_pairs32", "bgca_pair_stats", "bgca_reduce_bgc", "bgca_score_all_host",
     "bgca_last_launches", "bgca_last_dp_ms", "bgca_last_pack_ms", "bgca_dpx_probe",
 )
@@ -72,11 +72,12 @@ def load_library():
     lib.bgca_destroy.argtypes = [vp]
     lib.bgca_set_scoring.argtypes = [vp, vp, i32, i32, i32]
     lib.bgca_pack.argtypes = [vp, vp, vp, i32, vp, vp, i32, i32, i32, vp]
+    lib.bgca_pack_append.argtypes = [vp, vp, vp, i32, vp, vp, i32, i32, vp]
     lib.bgca_packed_bytes.argtypes = [vp]
     lib.bgca_packed_bytes.restype = i64
     lib.bgca_get_packed.argtypes = [vp, vp, vp, vp, vp]
     lib.bgca_plan.argtypes = [vp, i32, i32, i32, i32, P(PlanInfo)]
-    lib.bgca_plan_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, i64,
+    lib.bgca_plan_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, i64,
                                    P(i64), P(PlanInfo)]
     lib.bgca_score.argtypes = [vp, vp, vp, vp, i32, vp]
     lib.bgca_score_pairs32.argtypes = [vp, vp, vp, i64, vp, vp]
@@ -134,7 +135,7 @@ def concat_ascii(seqs: Sequence[str]):
 
 
 def plan_host(len_sorted, type_sorted=None, role_sorted=None, *, same_type_only=False, cross_only=False,
-              mode=MODE_LOCAL, max_abs_sub=11, open_gap=-12, extend_gap=-1, rank=0, world=1):
+              n_db_first=0, mode=MODE_LOCAL, max_abs_sub=11, open_gap=-12, extend_gap=-1, rank=0, world=1):
     """Host-only K6 planner (no CUDA).  Returns (tiles structured array, info dict).
     Inputs are in SORTED order: by type, then role (0 query / 1 database), then length."""
     lib = load_library()
@@ -144,7 +145,7 @@ def plan_host(len_sorted, type_sorted=None, role_sorted=None, *, same_type_only=
     n_tiles = ctypes.c_int64(0)
     info = PlanInfo()
     args = (_np_ptr(lens), _np_ptr(types), _np_ptr(roles), len(lens), int(same_type_only), int(cross_only),
-            mode, max_abs_sub, open_gap, extend_gap, rank, world)
+            int(n_db_first), mode, max_abs_sub, open_gap, extend_gap, rank, world)
     _check(lib.bgca_plan_host(*args, None, 0, ctypes.byref(n_tiles), ctypes.byref(info)))
     tiles = (Tile * max(1, n_tiles.value))()
     _check(lib.bgca_plan_host(*args, ctypes.cast(tiles, ctypes.c_void_p), n_tiles.value,
@@ -240,6 +241,29 @@ class Engine:
         self.n_bgc = int(n_bgc) if bgcs is not None else 0
         self.plan_info = None
 
+    def pack_append(self, seqs: Sequence[str], type_of_seq=None, bgc_of_seq=None, n_bgc_total: int = 0):
+        """Append a query set behind the batch packed earlier (which stays resident as the database);
+        a later call replaces the previous query set.  ORIGINAL indices afterwards: [database | queries]."""
+        ascii_, offsets = concat_ascii(seqs)
+        n_new = len(offsets) - 1
+        types = None if type_of_seq is None else np.ascontiguousarray(type_of_seq, dtype=np.int32)
+        bgcs = None if bgc_of_seq is None else np.ascontiguousarray(bgc_of_seq, dtype=np.int32)
+        for a in (types, bgcs):
+            if a is not None and len(a) != n_new:
+                raise ValueError("type_of_seq / bgc_of_seq must have one entry per sequence")
+        ascii_ = np.ascontiguousarray(ascii_, dtype=np.uint8)
+        n_db = self.n - self.n_query if self.n_query else self.n
+        with self.torch.cuda.device(self.tdev):
+            _check(self._lib.bgca_pack_append(self._h, _np_ptr(ascii_) if ascii_.size else ctypes.c_void_p(1),
+                                              _np_ptr(offsets), n_new, _np_ptr(types), _np_ptr(bgcs),
+                                              int(n_bgc_total), 0, self._stream()))
+        self.n = n_db + n_new
+        self.n_query = n_new
+        self.cross = False
+        if bgcs is not None:
+            self.n_bgc = int(n_bgc_total)
+        self.plan_info = None
+
     def get_packed(self):
         nbytes = int(self._lib.bgca_packed_bytes(self._h))
         codes = np.zeros(nbytes, dtype=np.uint8)
@@ -250,7 +274,9 @@ class Engine:
         return codes, offs, order
 
     # ---- K6 ------------------------------------------------------------------
-    def plan(self, same_type_only: bool = False, rank: int = 0, world: int = 1, cross_only: bool = False) -> dict:
+    def plan(self, same_type_only: bool = False, rank: int = 0, world: int = 1, cross_only=False) -> dict:
+        """cross_only: False | True | 2 (2 = cross pairs + query self pairs only, for a persistent
+        database whose self scores the caller already holds)."""
         info = PlanInfo()
         _check(self._lib.bgca_plan(self._h, int(same_type_only), int(cross_only), int(rank), int(world),
                                    ctypes.byref(info)))

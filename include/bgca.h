@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define BGCA_VERSION 103
+#define BGCA_VERSION 104
 
 #define BGCA_MODE_LOCAL 0  /* Smith-Waterman/Gotoh, result = best cell, >= 0        */
 #define BGCA_MODE_GLOBAL 1 /* Needleman-Wunsch/Gotoh, end gaps cost like internal   */
@@ -100,6 +100,19 @@ int bgca_pack(bgca_engine *e, const uint8_t *ascii, const int64_t *offsets, int3
               const int32_t *type_of_seq, const int32_t *bgc_of_seq, int32_t n_bgc,
               int32_t n_query, int32_t ascii_on_device, void *stream);
 
+/* Persistent database ("a new set of BGCs against a precomputed database",
+ * BGClib/Readme.md:18): keeps the batch packed by bgca_pack(..., n_query = 0) resident in HBM
+ * as a database and appends n_new query sequences behind it (a later call replaces the previous
+ * query set; only the queries are uploaded and encoded).  Afterwards the ORIGINAL index space is
+ * [database | queries]: query i is sequence n_database + i, outputs of bgca_score() after a
+ * cross plan are scores[n_new x n_database], rowbest[(n_database + n_new) x n_bgc_total],
+ * selfsc[n_database + n_new].  type_of_seq / bgc_of_seq must be given exactly when they were
+ * given for the database (same type-id space; query BGC indices continue after the
+ * database's, n_bgc_total = all of them). */
+int bgca_pack_append(bgca_engine *e, const uint8_t *ascii, const int64_t *offsets, int32_t n_new,
+                     const int32_t *type_of_seq, const int32_t *bgc_of_seq, int32_t n_bgc_total,
+                     int32_t ascii_on_device, void *stream);
+
 /* Introspection of the packed batch (host outputs; any pointer may be NULL).
  * codes_out must hold bgca_packed_bytes() bytes. */
 int64_t bgca_packed_bytes(const bgca_engine *e);
@@ -109,8 +122,10 @@ int bgca_get_packed(const bgca_engine *e, uint8_t *codes_out, int64_t *offsets_s
 /* K6 tile scheduler.  Enumerates the upper-triangular pair matrix (i<=j, self
  * pairs included) as tiles, optionally only within a domain type, and assigns
  * tiles to `world` ranks by longest-processing-time on the exact cell count.
- * cross_only != 0 (needs n_query at pack time): only query x database pairs are planned,
- * plus the self pair of every sequence (the similarity is normalised with self scores).
+ * cross_only != 0 (needs n_query at pack time, or queries appended with bgca_pack_append):
+ * only query x database pairs are planned, plus the self pair of every sequence (the
+ * similarity is normalised with self scores); cross_only == 2 leaves out the self pairs of a
+ * persistent database (the caller keeps its self scores from an earlier run).
  * bgca_plan keeps this rank's tiles on the device for bgca_score(). */
 int bgca_plan(bgca_engine *e, int32_t same_type_only, int32_t cross_only, int32_t rank, int32_t world,
               bgca_plan_info *info);
@@ -119,7 +134,9 @@ int bgca_plan(bgca_engine *e, int32_t same_type_only, int32_t cross_only, int32_
  * lengths/types; writes up to `capacity` tiles of `rank` and the tile count.
  * Used by the CPU tests of the scheduler. */
 int bgca_plan_host(const int32_t *len_sorted, const int32_t *type_sorted, const int32_t *role_sorted,
-                   int32_t n, int32_t same_type_only, int32_t cross_only, int32_t mode,
+                   int32_t n, int32_t same_type_only, int32_t cross_only,
+                   int32_t n_db_first /* > 0: sorted [0, n_db_first) is a persistent database */,
+                   int32_t mode,
                    int32_t max_abs_sub, int32_t open, int32_t extend,
                    int32_t rank, int32_t world,
                    bgca_tile *tiles_out, int64_t capacity, int64_t *n_tiles_out,

@@ -606,3 +606,37 @@ def test_outputs_stay_inside_their_buffers():
             assert (t[0] == SENT).all() and (t[-1] == SENT).all()
         cm = oracle.MODE_LOCAL if mode == "local" else oracle.MODE_GLOBAL
         assert (big[1:n + 1].cpu().numpy() == oracle.all_pairs(seqs, mode=cm)).all()
+
+
+@pytest.mark.parametrize("same_type_only", [True, False])
+def test_persistent_packed_database(af293, ks_records, same_type_only):
+    """PackedDatabase: the database stays packed on the device, query sets are appended behind it.
+    Results equal the one-shot query-vs-database call (itself checked against the oracle), for two
+    different query sets in a row; a bad query leaves the database usable."""
+    from bgclib_b200 import PackedDatabase
+    col = _af293_collection(af293, ks_records)
+    ids = list(col.bgcs)
+    dcol, q1, q2 = type(col)(), type(col)(), type(col)()
+    for k, b in enumerate(ids):
+        (q1 if k % 5 == 0 else q2 if k % 5 == 1 else dcol).bgcs[b] = col.bgcs[b]
+    db = PackedDatabase(dcol)
+    assert len(db) == len(extract(dcol))
+    for qcol in (q1, q2, q1):
+        got = bgc_similarity(qcol, database=db, same_type_only=same_type_only)
+        want = bgc_similarity(qcol, database=dcol, same_type_only=same_type_only)
+        assert got.bgc_ids == want.bgc_ids and got.db_bgc_ids == want.db_bgc_ids
+        assert (got.best == want.best).all() and (got.best_db == want.best_db).all()
+        assert (got.self_score == want.self_score).all() and (got.db_self_score == want.db_self_score).all()
+        assert (got.sim == want.sim).all()
+    # the rectangular domain-pair matrix from the same resident database, in both modes
+    qb, dbb = extract(q1), extract(dcol)
+    for mode, cm in (("local", oracle.MODE_LOCAL), ("global", oracle.MODE_GLOBAL)):
+        dps = domain_pair_scores(q1, database=db, mode=mode)
+        full = oracle.all_pairs(qb.sequences + dbb.sequences, mode=cm)
+        assert (dps.scores == full[: len(qb), len(qb):]).all()
+    with pytest.raises(ValueError, match="alphabet"):
+        bgc_similarity(["ACDEFGHIKL", "ACDUFG"], database=db)
+    again = bgc_similarity(q2, database=db, same_type_only=same_type_only)
+    assert (again.sim == bgc_similarity(q2, database=dcol, same_type_only=same_type_only).sim).all()
+    with pytest.raises(ValueError, match="scoring"):
+        bgc_similarity(q1, database=db, open_gap_score=-11)

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     lib = eng.load_library()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.bgca_version() == 103
+    assert lib.bgca_version() == 104
 
 
 def test_no_device_fails_loudly():
@@ -340,3 +340,36 @@ def test_row_block_covers_every_row_once():
                 assert 0 <= r0 <= r1 <= n and r1 - r0 <= blk and blk * world >= n
                 seen += list(range(r0, r1))
             assert seen == list(range(n))
+
+
+def test_planner_persistent_database_layout():
+    """n_db_first: database in front (sorted by type, length), queries appended behind it.  Every
+    query x database pair of the same type exactly once, plus the self pairs (all of them with
+    cross_only=1, the queries' only with cross_only=2)."""
+    rng = np.random.default_rng(11)
+    d_types = np.sort(rng.integers(0, 4, 90)).astype(np.int32)
+    d_lens = np.concatenate([np.sort(rng.integers(40, 500, int((d_types == t).sum()))) for t in range(4)]).astype(np.int32)
+    q_types = np.sort(rng.choice([0, 2, 3, 5], 17)).astype(np.int32)          # type 5 is not in the database
+    q_lens = np.concatenate([np.sort(rng.integers(40, 500, int((q_types == t).sum()))) for t in np.unique(q_types)]).astype(np.int32)
+    lens, types = np.concatenate([d_lens, q_lens]), np.concatenate([d_types, q_types])
+    roles = np.concatenate([np.ones(90, np.int32), np.zeros(17, np.int32)])
+    nd, n = 90, 107
+    for same_type in (True, False):
+        for cross in (1, 2):
+            seen = []
+            for r in range(3):
+                tiles, info = plan_host(lens, types, roles, same_type_only=same_type, cross_only=cross,
+                                        n_db_first=nd, rank=r, world=3)
+                for t in tiles:
+                    for s in range(t["s_begin"], t["s_end"]):
+                        for q in (t["qa"], t["qb"]):
+                            if q < 0:
+                                continue
+                            if q == s or (q >= nd) != (s >= nd):            # what emit_pair keeps in cross mode
+                                seen.append((q, s))
+            want = {(i, i) for i in range(nd if cross == 2 else 0, n)}
+            want |= {(q, d) for q in range(nd, n) for d in range(nd) if (not same_type or types[q] == types[d])}
+            assert len(seen) == len(set(seen)) and set(seen) == want
+            assert info["total_pairs"] == len(want)
+    with pytest.raises(ValueError):
+        plan_host(lens, types, roles, cross_only=False, n_db_first=nd)
