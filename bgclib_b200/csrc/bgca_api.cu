@@ -129,7 +129,7 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
     // subjects per alignment group and tile: 16 keeps >= 100 tiles per CTA slot on small
     // batches; larger batches take longer tiles (still > 150 per CTA slot at 10k sequences) so
     // that the tile list, and with it the plan time inside every end-to-end call, stays small
-    const int spg = std::min(64, std::max(kSubjectsPerGroup, n / 300));
+    int spg = std::min(64, std::max(kSubjectsPerGroup, n / 300));
 
     // exact accounting of unique pairs (i<=j) per tile
     auto tile_pairs = [&](const bgca_tile &T, int64_t &pairs, int64_t &cells) {
@@ -179,7 +179,10 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
     };
     if (!small_plan) R.tiles.reserve(((size_t)n * ((size_t)n / (2 * 128 * (size_t)spg) + 2) / 2) / (size_t)world + 64);
 
+    bool counting = false;          // pre-pass of cross plans: only add up the subjects visited
+    int64_t visits = 0;
     auto self_tile = [&](int qa, int qb) {
+        if (counting) return;
         const int La = len[qa], Lb = (qb >= 0) ? len[qb] : 0;
         const int Lq = std::max(La, Lb);
         bgca_tile T{};
@@ -196,6 +199,7 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
         const int Lq = std::max(La, Lb);
         const int S = te - sub0;
         if (S <= 0) return;
+        if (counting) { visits += S; return; }
         const int variant = pick_variant(Lq, mode, S);
         const int G = variant >> 8;
         // subjects per tile: ~spg per alignment group (= subject stream) of the CTA,
@@ -216,6 +220,7 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
         }
     };
 
+    auto generate = [&]() {
     int tb = 0;
     if (cross_only && n_db_first > 0) {
         // persistent database in front, queries behind: every query type block meets the
@@ -274,6 +279,17 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
         }
         tb = te;
     }
+    };   // generate
+    if (cross_only) {
+        // a few queries against a large database would otherwise make a few very long tiles: size
+        // the tiles so that every CTA slot of every rank still gets >= 16 of them
+        counting = true;
+        generate();
+        counting = false;
+        const int64_t target_tiles = 16LL * 2 * 148 * world;
+        spg = (int)std::max<int64_t>(2, std::min<int64_t>(spg, visits / (target_tiles * 16)));
+    }
+    generate();
 
     if (small_plan) {
         std::vector<int> idx(all.size());
