@@ -280,9 +280,9 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
         tb = te;
     }
     };   // generate
-    if (cross_only) {
-        // a few queries against a large database would otherwise make a few very long tiles: size
-        // the tiles so that every CTA slot of every rank still gets >= 16 of them
+    if (cross_only || small_plan) {
+        // a few queries against a large database, or a small batch, would otherwise make a few
+        // very long tiles: size them so that every CTA slot of every rank still gets >= 16
         counting = true;
         generate();
         counting = false;
