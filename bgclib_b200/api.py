@@ -80,9 +80,19 @@ def row_block(n: int, rank: int, world: int):
     return blk, r0, min(n, r0 + blk)
 
 
+def _check_batch(b: DomainBatch) -> DomainBatch:
+    """Type keys and BGC ids are identities: a hand-built batch with repeated names would be
+    merged wrongly with a second batch (query vs database)."""
+    if len(set(b.type_names)) != len(b.type_names):
+        raise ValueError("DomainBatch.type_names must be unique")
+    if len(set(b.bgc_ids)) != len(b.bgc_ids):
+        raise ValueError("DomainBatch.bgc_ids must be unique")
+    return b
+
+
 def _as_batch(source, unit, cbp_only, alias, domain_types) -> DomainBatch:
     if isinstance(source, DomainBatch):
-        return source
+        return _check_batch(source)
     return extract(source, unit=unit, cbp_only=cbp_only, alias=alias, domain_types=domain_types)
 
 

@@ -142,7 +142,8 @@ def mixed_collection(n_bgc: int, seed: int, type_weights: dict, dom_lo: int = 8,
         perm = rng.permutation(len(idx))
         for dst, src in zip(idx, perm):
             seqs[dst] = members[src]
-    tn = ["KS" if k == "KS420" else k for k in names]
+    # display names; type keys must stay unique (they are the identity of a type in the API)
+    tn = ["KS+KS_C" if k == "KS420" else k for k in names]
     return _assemble(seqs, types, tn, bgcs, n_bgc, name)
 
 

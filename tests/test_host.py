@@ -373,3 +373,14 @@ def test_planner_persistent_database_layout():
             assert info["total_pairs"] == len(want)
     with pytest.raises(ValueError):
         plan_host(lens, types, roles, cross_only=False, n_db_first=nd)
+
+
+def test_hand_built_batches_need_unique_type_keys_and_bgc_ids():
+    from bgclib_b200.api import _as_batch
+    from bgclib_b200.extract import DomainBatch
+    ok = DomainBatch(["ACD", "ACE"], [], ["b0", "b1"], np.array([0, 1], np.int32), ["KS", "AT"], np.array([0, 1], np.int32))
+    assert _as_batch(ok, "domain", True, None, None) is ok
+    for bad in (DomainBatch(["ACD", "ACE"], [], ["b0", "b1"], np.array([0, 1], np.int32), ["KS", "KS"], np.array([0, 1], np.int32)),
+                DomainBatch(["ACD", "ACE"], [], ["b0", "b0"], np.array([0, 1], np.int32), ["KS", "AT"], np.array([0, 1], np.int32))):
+        with pytest.raises(ValueError, match="unique"):
+            _as_batch(bad, "domain", True, None, None)
