@@ -16,6 +16,7 @@ Inputs
   --db-fasta / --db-bgccase   score the input against this database instead of against itself.
 Outputs (next to --out, TSV like write_metadata's tables, BGCtoolkit.py:1045-1137)
   <out>.bgc_similarity.tsv   BGC x BGC similarity, header row/column = BGC identifiers
+  <out>.bgc_distance.tsv     1 - similarity (the "distance calculation" of BGClib/Readme.md:16-18)
   <out>.bgc_best.tsv         the integer numerators best[a,b]
   <out>.domain_scores.npy + <out>.domain_index.tsv    (with --domain-scores)
 """
@@ -159,6 +160,7 @@ def main(argv=None):
     res = api.bgc_similarity(batch, database=db, same_type_only=not args.all_types, **gap)
     cols = res.db_bgc_ids if db is not None else res.bgc_ids
     write_matrix_tsv(f"{out}.bgc_similarity.tsv", res.sim, res.bgc_ids, cols, lambda v: repr(float(v)))
+    write_matrix_tsv(f"{out}.bgc_distance.tsv", 1.0 - res.sim, res.bgc_ids, cols, lambda v: repr(float(v)))
     write_matrix_tsv(f"{out}.bgc_best.tsv", res.best, res.bgc_ids, cols, lambda v: str(int(v)))
     if args.domain_scores:
         dps = api.domain_pair_scores(batch, database=db, mode=args.mode, same_type_only=not args.all_types, **gap)

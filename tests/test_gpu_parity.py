@@ -463,6 +463,9 @@ def test_cli_end_to_end(tmp_path, ks_records, af293):
     want, _, _, _ = oracle.bgc_similarity_np(oracle.all_pairs(seqs), bgc_of, np.zeros(15, int), len(ids))
     assert (sim == want).all()
     assert (np.load(tmp_path / "af293.domain_scores.npy") == oracle.all_pairs(seqs)).all()
+    dist_rows = (tmp_path / "af293.bgc_distance.tsv").read_text().splitlines()
+    dmat = np.array([[float(x) for x in r.split("\t")[1:]] for r in dist_rows[1:]])
+    assert (dmat == 1.0 - want).all() and (np.diag(dmat) == 0).all()
     # query-vs-database through the CLI
     assert cli.main(["--fasta", str(fa), "--db-fasta", str(fa), "--out", str(tmp_path / "x")]) == 0
 
