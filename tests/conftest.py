@@ -12,6 +12,13 @@ GOLDEN = ROOT / "tests" / "golden"
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # a fresh checkout has no libbgca.so (built artefacts are git-ignored): build it once, as
+    # __graft_entry__.build() does; nvcc cross-compiles without a GPU
+    from bgclib_b200 import build as _build
+    if _build.is_stale():
+        import shutil
+        if shutil.which(_build.NVCC) or Path(_build.NVCC).exists():
+            _build.build(verbose=True)
 
 
 def pytest_collection_modifyitems(config, items):
