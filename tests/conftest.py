@@ -15,7 +15,7 @@ def pytest_configure(config):
     # a fresh checkout has no libbgca.so (built artefacts are git-ignored): build it once, as
     # __graft_entry__.build() does; nvcc cross-compiles without a GPU
     from bgclib_b200 import build as _build
-    if _build.is_stale():
+    if not _build.LIB.exists():
         import shutil
         if shutil.which(_build.NVCC) or Path(_build.NVCC).exists():
             _build.build(verbose=True)
