@@ -13,6 +13,17 @@ weak scaling: round(10000*sqrt(N)) domains from the same generator, so the cells
 per GPU stay constant.  metric = GCUPS = 1e9 DP cells/s over the UNIQUE pairs
 with true lengths (padding, the redundant mirrored half-pairs and wind-up lanes
 are not credited).
+
+After the timed loop the same process runs, untimed for the headline but reported in the same
+JSON line:
+  "fused"          north_star's end product on ONE fixed collection at every N (strong scaling):
+                   BASELINE.json configs[3] — 60 601 mixed domains (70-600 aa) in 2 500 BGCs,
+                   same-type pairs — scored with the fused rowbest epilogue, combined with two
+                   NCCL all-reduce(max) and reduced to the BGC x BGC similarity; at N = 8 also
+                   one step of configs[4] (99 722 domains, every pair).
+  "parity_sample"  every rank checks 2 000 random entries of its score-matrix rows and 300 random
+                   rowbest entries of the fused result against the oracle, and rank 0 the whole
+                   best / self / sim of a 300-domain sub-collection (oracle = checker only).
 """
 from __future__ import annotations
 
@@ -37,6 +48,7 @@ N1_DOMAINS = 10_000
 SEED = 20260103
 ALG_LANE_OPS_PER_CELL = 3.0   # local, s16x2: 6 DPX/ALU ops per 2 cells
 ALU_LANES_PER_CLK_SM = 64     # alu pipe: 16 lanes/clk/SMSP x 4 (B300_MICROARCH.md "Pipe rates")
+ISSUE_LANES_PER_CLK_SM = 128  # issue limit: one warp instruction per clock per scheduler x 4
 
 
 def workload(n_gpus: int, n_override: int | None):
@@ -44,6 +56,11 @@ def workload(n_gpus: int, n_override: int | None):
     n = n_override or int(round(N1_DOMAINS * math.sqrt(n_gpus)))
     col = synth.ks_like(n, seed=SEED)
     return col, f"{n} synthetic KS-like domains (L~N(420,15) in [360,480], seed {SEED}), all pairs i<=j"
+
+
+def bench_config(wl: str) -> dict:
+    """The `config` object — identical keys and values in both arms."""
+    return {"workload": wl, "mode": "local", "matrix": "BLOSUM62", "open": -12, "extend": -1}
 
 
 class ClockSampler:
@@ -131,13 +148,13 @@ def run_reference(args):
             vals.append(g); secs.append(dt); pps = p
     v = statistics.mean(vals)
     line = {
-        "impl": "reference", "metric": "GCUPS", "value": v, "unit": "GCUPS (1e9 DP cells/s)",
+        "impl": "reference", "metric": "GCUPS", "value": v, "unit": "GCUPS",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * statistics.mean(secs), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": wl, "mode": "local", "matrix": "BLOSUM62", "open": -12, "extend": -1,
-                   "note": "CPU restatement of Biopython PairwiseAligner.score semantics (oracle port); "
-                           "the reference has no aligner of its own; each step = a bounded sample"},
+        "config": bench_config(wl),
+        "note": "CPU restatement of Biopython PairwiseAligner.score semantics (oracle port); the reference "
+                "has no aligner of its own; each step = a bounded sample of the workload",
         "pairs_per_s": pps,
         "cpu_baseline": {"value": v, "unit": "GCUPS", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -145,6 +162,134 @@ def run_reference(args):
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+def _all_sum(dist, dev, *vals):
+    """Sum of small integers over ranks (identity without a process group)."""
+    import torch
+    t = torch.tensor(list(vals), dtype=torch.int64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return [int(v) for v in t.tolist()]
+
+
+def matrix_parity_sample(col, result, row0, rng, m=2000):
+    """m random entries (i, j) of this rank's rows of the score matrix against the oracle."""
+    import oracle
+    rows, n = result.shape
+    li = rng.integers(0, rows, size=m)
+    j = rng.integers(0, n, size=m)
+    got = result[li, j].cpu().numpy()
+    want = oracle.pair_list(col.sequences(), li + row0, j, nthreads=1)
+    return m, int((got != want).sum())
+
+
+def rowbest_parity_sample(col, rowbest, rng, m=300):
+    """m random entries rowbest[d, b] of the combined fused result against their definition
+    (SURVEY.md App. D): max of the oracle's local scores of d with the same-type domains of b."""
+    import oracle
+    n, B = rowbest.shape
+    d = rng.integers(0, n, size=m)
+    b = rng.integers(0, B, size=m)
+    order = np.argsort(col.bgc_of_seq, kind="stable")
+    start = np.searchsorted(col.bgc_of_seq[order], np.arange(B + 1))
+    pi, pj, seg = [], [], []
+    for k in range(m):
+        mem = order[start[b[k]]:start[b[k] + 1]]
+        mem = mem[col.type_of_seq[mem] == col.type_of_seq[d[k]]]
+        pi.extend([d[k]] * len(mem)); pj.extend(mem.tolist()); seg.extend([k] * len(mem))
+    want = np.zeros(m, dtype=np.int64)
+    if pi:
+        sc = oracle.pair_list(col.sequences(), np.asarray(pi), np.asarray(pj), nthreads=1)
+        np.maximum.at(want, np.asarray(seg), sc)
+    got = rowbest[d, b].cpu().numpy()
+    return len(pi), m, int((got != want).sum())
+
+
+def fused_leg(eng, col, dist, rank, world, dev, steps, warm, same_type_only, check_rng=None):
+    """north_star's end product on a fixed collection (strong scaling): zero rowbest/selfsc ->
+    DP kernels with the fused rowbest epilogue on this rank's tiles -> all-reduce(max) x2 ->
+    BGC reduction.  Timed with CUDA events on the launch stream, max over ranks."""
+    import torch
+    n, B = len(col), col.n_bgc
+    eng.pack_ascii(col.ascii, col.offsets, col.type_of_seq, col.bgc_of_seq, B)
+    plan = eng.plan(same_type_only=same_type_only, rank=rank, world=world)
+    rowbest = torch.zeros((n, B), dtype=torch.int32, device=dev)
+    selfsc = torch.zeros((n,), dtype=torch.int32, device=dev)
+    out = {}
+
+    def step():
+        rowbest.zero_()
+        selfsc.zero_()
+        eng.score(rowbest=rowbest, selfsc=selfsc, type_check=False)
+        if dist is not None:
+            dist.all_reduce(rowbest, op=dist.ReduceOp.MAX)
+            dist.all_reduce(selfsc, op=dist.ReduceOp.MAX)
+        out["r"] = eng.reduce_bgc(rowbest, selfsc)
+
+    launches = 0
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+        launches += eng.last_launches() + 2
+    e1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    dp = torch.tensor([eng.last_dp_ms()], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(dp, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    sim = out["r"][0]
+    res = {"workload": f"{col.name}: {n} domains, {B} BGCs, "
+                       f"{'same-type pairs' if same_type_only else 'every pair'} (seed fixed)",
+           "scaling": "strong", "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms,
+           "gcups": plan["total_cells"] / (ms * 1e-3) / 1e9, "pairs_per_s": plan["total_pairs"] / (ms * 1e-3),
+           "pairs": plan["total_pairs"], "cells": plan["total_cells"], "dp_ms_max_rank": float(dp.item()),
+           "collective_bytes": int(rowbest.nbytes + selfsc.nbytes) if world > 1 else 0,
+           "collective": "2 x NCCL all-reduce(max) over int32 rowbest[n, B] and selfsc[n]" if world > 1 else None,
+           "gpu_launches": launches,
+           "sim_diag_ones": bool((torch.diagonal(sim) == 1).all().item()),
+           "sim_symmetric": bool((sim == sim.T).all().item())}
+    chk = None
+    if check_rng is not None:
+        chk = rowbest_parity_sample(col, rowbest, check_rng)
+    del rowbest, selfsc
+    return res, chk
+
+
+def subcollection_parity(eng, col, dist, rank, world, dev, n_sub=300):
+    """Fused similarity of the first n_sub domains through every rank; rank 0 compares best, self
+    and sim with the oracle's plain-loop statement.  Returns (entries checked, mismatches)."""
+    import torch
+    import oracle
+    sub = col.subset(n_sub)
+    B = int(sub.bgc_of_seq.max()) + 1
+    eng.pack_ascii(sub.ascii, sub.offsets, sub.type_of_seq, sub.bgc_of_seq, B)
+    eng.plan(same_type_only=True, rank=rank, world=world)
+    rowbest = torch.zeros((n_sub, B), dtype=torch.int32, device=dev)
+    selfsc = torch.zeros((n_sub,), dtype=torch.int32, device=dev)
+    eng.score(rowbest=rowbest, selfsc=selfsc, type_check=False)
+    if dist is not None:
+        dist.all_reduce(rowbest, op=dist.ReduceOp.MAX)
+        dist.all_reduce(selfsc, op=dist.ReduceOp.MAX)
+    sim, best, selfsum = eng.reduce_bgc(rowbest, selfsc)
+    if rank != 0:
+        return 0, 0
+    nth = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    sc = oracle.all_pairs(sub.sequences(), nthreads=nth)
+    o_sim, o_best, o_self, _ = oracle.bgc_similarity_np(sc, sub.bgc_of_seq, sub.type_of_seq, B)
+    bad = int((best.cpu().numpy() != o_best).sum() + (selfsum.cpu().numpy() != o_self).sum() +
+              (sim.cpu().numpy() != o_sim).sum())
+    return 2 * B * B + B, bad
 
 
 def main():
@@ -159,6 +304,11 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--probe", action="store_true", help="(default at N=1) run the DPX issue-rate microbenchmark")
     ap.add_argument("--no-probe", action="store_true", help="skip the DPX issue-rate microbenchmark")
+    ap.add_argument("--no-fused", action="store_true", help="skip the fused BGC-similarity leg (configs[3])")
+    ap.add_argument("--fused-steps", type=int, default=3)
+    ap.add_argument("--fused-config5", action="store_true",
+                    help="also one step of configs[4] (99 722 domains, every pair); default at N = 8")
+    ap.add_argument("--no-parity-sample", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -234,6 +384,18 @@ def main():
     ms_per_step = float(elapsed_ms.item()) / args.steps
     total_cells, total_pairs = plan["total_cells"], plan["total_pairs"]
     gcups = total_cells / (ms_per_step * 1e-3) / 1e9
+    pdist = dist if world > 1 else None
+
+    # ---- parity sample of the matrix leg: this rank's rows of the result just timed -------------
+    parity = {"pairs": 0, "mismatches": 0}
+    if not args.no_parity_sample:
+        rng = np.random.default_rng(1000 + rank)
+        m, bad = matrix_parity_sample(col, scores if world == 1 else mine[: r1 - r0], 0 if world == 1 else r0, rng)
+        m, bad = _all_sum(pdist, dev, m, bad)
+        parity["matrix_leg"] = {"pairs": m, "mismatches": bad,
+                                "what": "random (i, j) of each rank's rows of the timed result vs oracle.pair_list"}
+        parity["pairs"] += m
+        parity["mismatches"] += bad
 
     # ---- e2e: host buffers in, host matrix out, copies inside the timed region ----------------
     e2e = None
@@ -266,7 +428,7 @@ def main():
         t = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": total_cells / float(t.item()) / 1e9, "unit": "GCUPS (1e9 DP cells/s)",
+        e2e = {"value": total_cells / float(t.item()) / 1e9, "unit": "GCUPS",
                "h2d_bytes_per_step": int(col.ascii.nbytes + col.offsets.nbytes + 20 * n) * world,
                "d2h_bytes_per_step": int(4 * n * n) if world == 1 else int(4 * blk * world * n),
                "ms_per_step": 1e3 * float(t.item()),
@@ -305,7 +467,9 @@ def main():
             k5.append(e0.elapsed_time(e1))
         k1_ms, k5_ms = statistics.median(k1[1:]), statistics.median(k5[1:])
         k1_bytes = int(big.ascii.nbytes) + int(eng._lib.bgca_packed_bytes(eng._h))
-        k5_bytes = 4 * nb * Bb + 4 * nb + 8 * Bb * Bb + 8 * Bb + 3 * 8 * Bb * Bb
+        # rowbest read once, best written once, sim written once (the sim kernel's
+        # reads of best / its transpose are re-reads of data just written, not algorithmic bytes)
+        k5_bytes = 4 * nb * Bb + 8 * Bb * Bb + 8 * Bb * Bb
         stages = {"workload": f"{nb} synthetic NRPS/PKS domains in {Bb} BGCs (BASELINE config 5), cold L2",
                   "peak_gbs": hbm_peak, "peak_source": peak_src,
                   "k1_pack": {"ms": k1_ms, "algorithmic_bytes": k1_bytes, "gbs": k1_bytes / k1_ms / 1e6,
@@ -313,6 +477,34 @@ def main():
                   "k5_bgc_reduce": {"ms": k5_ms, "algorithmic_bytes": k5_bytes, "gbs": k5_bytes / k5_ms / 1e6,
                                     "frac": k5_bytes / k5_ms / 1e6 / hbm_peak}}
         del rowbest, selfsc, flush, ascii_dev
+        eng.pack_ascii(col.ascii, col.offsets)                 # leave the engine on the bench workload
+
+    # ---- fused BGC similarity, strong scaling on one fixed collection (configs[3]; [4] at N = 8) ----
+    fused = fused5 = None
+    if not args.no_fused:
+        from bgclib_b200 import synth as _synth
+        col4 = _synth.mibig_scale(2500)
+        frng = None if args.no_parity_sample else np.random.default_rng(2000 + rank)
+        fused, chk = fused_leg(eng, col4, pdist, rank, world, dev, max(1, args.fused_steps), 1, True, frng)
+        if chk is not None:
+            npairs, m, bad = _all_sum(pdist, dev, *chk)
+            parity["fused_rowbest"] = {"entries": m, "pairs": npairs, "mismatches": bad,
+                                       "what": "random rowbest[d, b] of the combined fused result vs the max of "
+                                               "oracle.pair_list over the same-type domains of BGC b"}
+            parity["pairs"] += npairs
+            parity["mismatches"] += bad
+            ent, bad = subcollection_parity(eng, col4, pdist, rank, world, dev)
+            ent, bad = _all_sum(pdist, dev, ent, bad)
+            parity["fused_subcollection"] = {"entries": ent, "mismatches": bad,
+                                             "what": "best, self, sim of the first 300 domains (all ranks) vs "
+                                                     "oracle.all_pairs + oracle.bgc_similarity_np on rank 0"}
+            parity["pairs"] += 300 * 301 // 2
+            parity["mismatches"] += bad
+        del col4
+        if args.fused_config5 or world >= 8:
+            col5 = _synth.nrps_pks_100k(4167)
+            fused5, _ = fused_leg(eng, col5, pdist, rank, world, dev, 1, 0, False, None)
+            del col5
         eng.pack_ascii(col.ascii, col.offsets)                 # leave the engine on the bench workload
 
     if rank == 0:
@@ -324,16 +516,23 @@ def main():
             pass
         sm_max = float(peaks.get("sm_max_mhz", clocks.get("sm_max_mhz") or 1965.0))
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-        peak_nominal = n_sm * ALU_LANES_PER_CLK_SM * sm_max * 1e6 / 1e12        # Tlane-op/s
+        # Peak = the sm_100a issue-rate limit north_star names: one warp instruction per clock per
+        # scheduler = 128 lanes/clk/SM, at the maximum SM clock.  (The alu pipe alone takes half of
+        # that; the kernel puts its packed adds on the fma pipe, so the alu-pipe nominal is not a
+        # ceiling for it — kept beside the fraction as frac_alu_pipe_nominal.)
+        peak_issue = n_sm * ISSUE_LANES_PER_CLK_SM * sm_max * 1e6 / 1e12        # Tlane-op/s
+        peak_alu = n_sm * ALU_LANES_PER_CLK_SM * sm_max * 1e6 / 1e12
         achieved = plan["cells"] * ALG_LANE_OPS_PER_CELL / (dp_ms[-1] * 1e-3) / 1e12
         roofline = {
-            "bound": "alu", "kernel": "gotoh_pair16_kernel<G,K,local> (all variants of one step)",
-            "achieved": achieved, "peak": peak_nominal, "unit": "Tlane-op/s", "frac": achieved / peak_nominal,
-            "peak_source": f"nominal ALU pipe: {n_sm} SMs x {ALU_LANES_PER_CLK_SM} lanes/clk x {sm_max:.0f} MHz "
-                           "(MEASURED_PEAKS.json holds no integer/DPX figure; see dpx_probe for the measured rate)",
+            "bound": "issue", "kernel": "gotoh_pair16_kernel<G,K,local> (all variants of one step)",
+            "achieved": achieved, "peak": peak_issue, "unit": "Tlane-op/s", "frac": achieved / peak_issue,
+            "peak_source": f"sm_100a issue rate: {n_sm} SMs x {ISSUE_LANES_PER_CLK_SM} lanes/clk x {sm_max:.0f} MHz "
+                           "(MEASURED_PEAKS.json holds no integer/DPX figure; B300_MICROARCH.md 'Instruction issue'; "
+                           "dpx_probe below measures the per-op rates)",
             "alg_lane_ops_per_cell": ALG_LANE_OPS_PER_CELL,
             "kernel_ms": dp_ms[-1], "kernel_gcups": plan["cells"] / (dp_ms[-1] * 1e-3) / 1e9,
-            "frac_at_observed_clock": achieved / (n_sm * ALU_LANES_PER_CLK_SM * sm_mhz * 1e6 / 1e12),
+            "frac_at_observed_clock": achieved / (n_sm * ISSUE_LANES_PER_CLK_SM * sm_mhz * 1e6 / 1e12),
+            "frac_alu_pipe_nominal": achieved / peak_alu,
             "traffic": None,
         }
         try:
@@ -362,17 +561,18 @@ def main():
             cpu = {"value": g, "unit": "GCUPS", "cores": cores, "kind": "port", "sample": desc,
                    "pairs_per_s": pps}
         line = {
-            "metric": "GCUPS", "value": gcups, "unit": "GCUPS (1e9 DP cells/s)", "n_gpus": world,
+            "metric": "GCUPS", "value": gcups, "unit": "GCUPS", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "s16x2", "data": "synthetic",
-            "config": {"workload": wl, "mode": "local", "matrix": "BLOSUM62", "open": -12, "extend": -1,
-                       "pairs": total_pairs, "cells": total_cells, "parallelism": f"tile-sharded x{world}",
-                       "l2": "each step rewrites the n*n int32 score matrix (400 MB at N=1) before the "
-                             "kernels, which evicts L2; DP inputs (4 MB of residues) are L2-resident by design",
-                       "tiles_rank0": plan["n_tiles"], "kernel_variants_rank0": plan["n_variants"]},
+            "config": bench_config(wl),
+            "pairs": total_pairs, "cells": total_cells, "parallelism": f"tile-sharded x{world}",
+            "l2": "each step rewrites the n*n int32 score matrix (400 MB at N=1) before the kernels, which "
+                  "evicts L2; DP inputs (4 MB of residues) are L2-resident by design",
+            "tiles_rank0": plan["n_tiles"], "kernel_variants_rank0": plan["n_variants"],
             "pairs_per_s": total_pairs / (ms_per_step * 1e-3),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu, "hbm_stages": stages,
+            "fused": fused, "fused_config5": fused5, "parity_sample": parity,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

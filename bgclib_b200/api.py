@@ -198,6 +198,8 @@ def bgc_similarity(source, *, database=None, matrix="BLOSUM62", open_gap_score=-
     """BGC x BGC similarity from local domain-pair scores:
 
         rowbest[d,b] = max{ s(d,e) : e in b, type(e) == type(d) }      (0 if none)
+                       (``same_type_only=False`` drops the type condition on purpose, SURVEY.md
+                       App. D: every domain of b is then a candidate partner of d)
         best[a,b]    = sum_{d in a} rowbest[d,b]
         self[a]      = sum_{d in a} s(d,d)
         sim[a,b]     = (best[a,b] + best[b,a]) / (self[a] + self[b])    (0/0 -> 0, sim[a,a] = 1)
@@ -258,17 +260,19 @@ def bgc_similarity(source, *, database=None, matrix="BLOSUM62", open_gap_score=-
         done = ckpt.load_into(rowbest, selfsc)
     plan = None
     for r in range(rounds):
+        if r in done:                       # finished before the interruption: nothing to plan or score
+            continue
         # round r of this rank = virtual rank (rank * rounds + r) of (world * rounds)
         part = eng.plan(same_type_only=same_type_only, rank=rank * rounds + r, world=world * rounds)
         plan = part if plan is None else {k: (plan[k] + part[k] if k in _PLAN_SUMS else part[k]) for k in part}
-        if r in done:
-            continue
         eng.score(rowbest=rowbest, selfsc=selfsc, type_check=False)
         done.add(r)
         if ckpt is not None:
             ckpt.save(rowbest, selfsc, done)
         if _stop_after_rounds is not None and len(done) >= _stop_after_rounds:
             raise KeyboardInterrupt(f"stopped after {len(done)} of {rounds} rounds (test hook)")
+    if plan is None:                        # every round came from the checkpoint
+        plan = {"resumed_rounds": len(done)}
     if dist is not None:
         dist.all_reduce(rowbest, op=dist.ReduceOp.MAX)
         dist.all_reduce(selfsc, op=dist.ReduceOp.MAX)

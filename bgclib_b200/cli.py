@@ -2,9 +2,16 @@
 sketches and leaves commented out (BGCtoolkit.py:157-161: "calculate protein similarity
 between each pair of BGCs"), as a stand-alone entry point:
 
-    python -m bgclib_b200.cli --fasta all_KS_domains.fasta --out results/af293
-    python -m bgclib_b200.cli --fasta new.fasta --db-fasta mibig_domains.fasta --out hits
-    python -m bgclib_b200.cli --bgccase AfumigatusAf293.bgccase --alias-tsv domains_alias.tsv --out af293
+    python -m bgclib_b200.cli --comparative --fasta all_KS_domains.fasta --out results/af293
+    python -m bgclib_b200.cli --comparative --fasta new.fasta --db-fasta mibig_domains.fasta --out hits
+    python -m bgclib_b200.cli --comparative --bgccase AfumigatusAf293.bgccase --bgclist order.tsv \
+        --alias-tsv domains_alias.tsv --out af293
+
+``--comparative`` is spelled as the reference sketches it; it is also what the tool does when
+neither it nor ``--domain-scores`` is given.  ``-l/--bgclist`` is the reference's tab-separated
+list (first column = BGC identifier, ``#`` comments; read_bgc_list, BGCtoolkit.py:331-358): it
+selects the BGCs compared and fixes the row order of the matrices, the way the stacked figure
+the flag was meant for takes its order from that file (BGCtoolkit.py:788-801, :818).
 
 Inputs
   --fasta      a domain FASTA as ``BGCtoolkit.py --cbt-fasta`` writes it (save_fasta,
@@ -122,6 +129,31 @@ def batch_from_bgccase(path, alias, cbp_only=True) -> DomainBatch:
     return extract(col, alias=alias, cbp_only=cbp_only)
 
 
+def read_bgc_list(path) -> List[str]:
+    """First column of the reference's --bgclist file (read_bgc_list, BGCtoolkit.py:331-358: tab
+    separated, '#' lines and blank lines skipped; the optional second column names a reference
+    protein for the figure and is not used here).  Order kept, repeats dropped."""
+    ids: List[str] = []
+    with open(path) as f:
+        for line in f:
+            if line[0] == "#" or line.strip() == "":
+                continue
+            b = line.split("\t")[0].strip()
+            if b and b not in ids:
+                ids.append(b)
+    if not ids:
+        raise SystemExit("Error: filter BGC list given but the file is empty...")
+    return ids
+
+
+def apply_bgc_list(batch: DomainBatch, ids: List[str]) -> DomainBatch:
+    known = set(batch.bgc_ids)
+    for b in ids:
+        if b not in known:       # the reference warns and goes on (BGCtoolkit.py:818)
+            print(f"\t--bgclist used but {b} not found in BGC data", file=sys.stderr)
+    return batch.select_bgcs([b for b in ids if b in known])
+
+
 def write_matrix_tsv(path, matrix, row_ids, col_ids, fmt):
     with open(path, "w") as f:
         f.write("BGC\t" + "\t".join(col_ids) + "\n")
@@ -136,6 +168,11 @@ def main(argv=None):
     ap.add_argument("--db-fasta")
     ap.add_argument("--db-bgccase")
     ap.add_argument("--alias-tsv")
+    ap.add_argument("--comparative", default=False, action="store_true",
+                    help="calculate protein similarity between each pair of BGCs (the switch "
+                         "BGCtoolkit.py:157-161 sketches); the default action of this tool")
+    ap.add_argument("-l", "--bgclist", help="tab-separated file, first column = BGC identifier: the BGCs to "
+                                            "compare and their order in the matrices (BGCtoolkit.py:86, :331-358)")
     ap.add_argument("--out", required=True)
     ap.add_argument("--mode", default="local", choices=["local", "global"], help="for --domain-scores")
     ap.add_argument("--open-gap-score", type=int, default=-12)
@@ -152,6 +189,10 @@ def main(argv=None):
         return batch_from_fasta(fasta) if fasta else batch_from_bgccase(case, alias, not args.all_proteins)
 
     batch = load(args.fasta, args.bgccase)
+    if args.bgclist:
+        batch = apply_bgc_list(batch, read_bgc_list(args.bgclist))
+        if len(batch) == 0:
+            raise SystemExit("Error: no BGC of --bgclist holds domain sequences")
     db = load(args.db_fasta, args.db_bgccase) if (args.db_fasta or args.db_bgccase) else None
     from . import api   # needs the GPU from here on
     out = Path(args.out)

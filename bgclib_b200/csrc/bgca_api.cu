@@ -125,6 +125,20 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
     PlanResult R;
     std::vector<int64_t> pre(n + 1, 0);
     for (int i = 0; i < n; ++i) pre[i + 1] = pre[i] + len[i];
+    // The packer sorts by (type, role, length): lengths are non-decreasing only inside one run.
+    // run_end[i] = end of the non-decreasing run that holds i, so the longest subject of any
+    // range is the maximum over the last elements of the few runs it crosses.
+    std::vector<int32_t> run_end(n);
+    for (int i = n - 1; i >= 0; --i) run_end[i] = (i + 1 < n && len[i + 1] >= len[i]) ? run_end[i + 1] : i + 1;
+    auto max_len_in = [&](int s0, int s1) {
+        int mx = 0;
+        for (int i = s0; i < s1;) {
+            const int e = std::min<int>(run_end[i], s1);
+            mx = std::max(mx, len[e - 1]);
+            i = e;
+        }
+        return mx;
+    };
 
     // subjects per alignment group and tile: 16 keeps >= 100 tiles per CTA slot on small
     // batches; larger batches take longer tiles (still > 150 per CTA slot at 10k sequences) so
@@ -214,7 +228,7 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
             bgca_tile T{};
             T.qa = qa; T.qb = qb; T.s_begin = s0; T.s_end = s1;
             T.variant = variant;
-            if (variant && !fits_int16(mode, max_abs_sub, open, extend, Lq, len[s1 - 1])) T.variant = 0;
+            if (variant && !fits_int16(mode, max_abs_sub, open, extend, Lq, max_len_in(s0, s1))) T.variant = 0;
             T.cells = (int64_t)(La + Lb) * (pre[s1] - pre[s0]);
             produce(T);
         }
@@ -636,27 +650,45 @@ try {
         return fail(BGCA_ERR_RANGE, "bgca_pack_append: n_bgc_total must be in 1..65535");
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(e->device));
-    if (e->n_db == 0) {                      // first query set: everything packed so far is the database
-        e->n_db = e->n;
-        e->db_bytes = (uint64_t)e->packed_bytes;
-    }
-    const int n_db = e->n_db;
+    // every host-side check comes before the engine is touched, so a rejected query set leaves
+    // the database exactly as it was
+    const int n_db = e->n_db ? e->n_db : e->n;
+    const uint64_t db_bytes = e->n_db ? e->db_bytes : (uint64_t)e->packed_bytes;
     if ((int64_t)n_db + n_new > 0x7FFFFFF0) return fail(BGCA_ERR_RANGE, "bgca_pack_append: too many sequences");
-    e->packed = false;
-    e->planned = false;
-
     std::vector<int32_t> len_new(n_new);
-    for (int i = 0; i < n_new; ++i) {
-        const int64_t l = offsets[i + 1] - offsets[i];
-        if (l < 0) return fail(BGCA_ERR_INVALID, "bgca_pack_append: offsets must be non-decreasing");
-        if (l == 0) return fail(BGCA_ERR_EMPTY, "sequence " + std::to_string(i) + " has zero length");
-        if (l > 65535) return fail(BGCA_ERR_RANGE, "sequence " + std::to_string(i) + " longer than 65535");
-        len_new[i] = (int32_t)l;
+    {
+        uint64_t bytes = db_bytes;
+        for (int i = 0; i < n_new; ++i) {
+            const int64_t l = offsets[i + 1] - offsets[i];
+            if (l < 0) return fail(BGCA_ERR_INVALID, "bgca_pack_append: offsets must be non-decreasing");
+            if (l == 0) return fail(BGCA_ERR_EMPTY, "sequence " + std::to_string(i) + " has zero length");
+            if (l > 65535) return fail(BGCA_ERR_RANGE, "sequence " + std::to_string(i) + " longer than 65535");
+            len_new[i] = (int32_t)l;
+            bytes += (uint64_t)((l + 1 + 15) & ~15);
+        }
+        if (bytes > 0xFFFFFFF0ull) return fail(BGCA_ERR_RANGE, "bgca_pack_append: packed batch exceeds 4 GiB");
     }
     if (bgc_of_seq)
         for (int i = 0; i < n_new; ++i)
             if (bgc_of_seq[i] < 0 || bgc_of_seq[i] >= n_bgc_total)
                 return fail(BGCA_ERR_INVALID, "bgca_pack_append: bgc_of_seq out of range");
+    e->n_db = n_db;                          // first query set: everything packed so far is the database
+    e->db_bytes = db_bytes;
+    e->packed = false;
+    e->planned = false;
+    // any failure from here on (allocation, upload, an illegal letter) puts the engine back on
+    // the bare database: the next bgca_pack_append starts over
+    struct Restore {
+        bgca_engine *e;
+        bool armed = true;
+        ~Restore()
+        {
+            if (!armed) return;
+            e->n = e->n_db; e->n_query = 0; e->packed_bytes = (int64_t)e->db_bytes; e->packed = true;
+            e->len.resize(e->n); e->type.resize(e->n); e->bgc.resize(e->n); e->role.resize(e->n);
+            e->seq_off.resize(e->n); e->order.resize(e->n); e->inv_order.resize(e->n);
+        }
+    } restore{e};
 
     // queries sorted by (type, length) among themselves, placed behind the database in BOTH
     // index spaces: sorted r = n_db + k  <->  original n_db + (position in the query list)
@@ -682,7 +714,6 @@ try {
         e->role[r] = 0;
         e->seq_off[r] = (uint32_t)off;
         off += (uint64_t)((len_new[o] + 1 + 15) & ~15);
-        if (off > 0xFFFFFFF0ull) return fail(BGCA_ERR_RANGE, "bgca_pack_append: packed batch exceeds 4 GiB");
     }
     e->n = n;
     e->n_query = n_new;
@@ -741,12 +772,11 @@ try {
     CUDA_TRY(cudaMemcpyAsync(&err, e->d_err.p, sizeof(err), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (err != ~0ULL) {
-        // a failed query set leaves the database intact: the next bgca_pack_append starts over
-        e->n = n_db; e->n_query = 0; e->packed_bytes = (int64_t)e->db_bytes; e->packed = true;
         const unsigned seq = (unsigned)(err >> 32) - (unsigned)n_db, pos = (unsigned)(err & 0xFFFFFFFFu);
         return fail(BGCA_ERR_ALPHABET, "sequence " + std::to_string(seq) + " contains a letter not in the "
                                        "alphabet ARNDCQEGHILKMFPSTWYVBZX* at position " + std::to_string(pos));
     }
+    restore.armed = false;
     e->packed = true;
     return BGCA_OK;
 } catch (const std::exception &ex) {
@@ -825,6 +855,10 @@ try {
     e->cross_planned = cross_only != 0;
     e->tiles.swap(R.tiles);
     e->plan_info = R.info;
+    // the persistent kernels of an earlier bgca_score() may still be reading d_tiles on the caller's
+    // stream or on the side streams: its closing event (recorded after the side streams joined)
+    // must have passed before the list is replaced or its buffer reallocated
+    if (e->timed) CUDA_TRY(cudaEventSynchronize(e->ev1));
     CUDA_TRY(e->d_tiles.reserve(e->tiles.size()));
     if (!e->tiles.empty())
         CUDA_TRY(cudaMemcpy(e->d_tiles.p, e->tiles.data(), sizeof(bgca_tile) * e->tiles.size(),
@@ -911,9 +945,17 @@ try {
             std::vector<int32_t> pq, ps;
             for (size_t i = b; i < en; ++i) {
                 const bgca_tile &T = e->tiles[i];
+                if (T.reserved) {            // self-only tile of a cross plan
+                    pq.push_back(T.qa); ps.push_back(T.qa);
+                    if (T.qb >= 0) { pq.push_back(T.qb); ps.push_back(T.qb); }
+                    continue;
+                }
+                // square plans list the mirrored pair (qb, s < qb) on the qa side already; cross
+                // plans pair queries with database subjects that may sort before OR behind them
+                // (a persistent database sits in front of its queries), so nothing is mirrored there
                 for (int s = T.s_begin; s < T.s_end; ++s) {
                     pq.push_back(T.qa); ps.push_back(s);
-                    if (T.qb >= 0 && s >= T.qb) { pq.push_back(T.qb); ps.push_back(s); }
+                    if (T.qb >= 0 && (e->cross_planned || s >= T.qb)) { pq.push_back(T.qb); ps.push_back(s); }
                 }
             }
             CUDA_TRY(e->d_pq.reserve(pq.size()));

@@ -49,6 +49,21 @@ class DomainBatch:
     def __len__(self):
         return len(self.sequences)
 
+    def select_bgcs(self, ids: Sequence[str]) -> "DomainBatch":
+        """The batch restricted to the BGCs named in ``ids``, in that order (the reading a
+        ``--bgclist`` file gets, BGCtoolkit.py:331-358); unknown ids raise KeyError."""
+        pos = {b: k for k, b in enumerate(self.bgc_ids)}
+        new_of_old = np.full(len(self.bgc_ids), -1, dtype=np.int32)
+        for k, b in enumerate(ids):
+            new_of_old[pos[b]] = k
+        keep = [i for i in range(len(self.sequences)) if new_of_old[self.bgc_of_seq[i]] >= 0]
+        recs = [DomainRecord(k, *(getattr(self.records[i], f) for f in
+                                 ("bgc_id", "protein_identifier", "domain_id", "type_key", "ali_from", "ali_to", "length")))
+                for k, i in enumerate(keep)]
+        return DomainBatch([self.sequences[i] for i in keep], recs, list(ids),
+                           new_of_old[self.bgc_of_seq[keep]].astype(np.int32), list(self.type_names),
+                           self.type_of_seq[keep].astype(np.int32), list(self.skipped))
+
     # ---- on-disk form (resumable / repeated runs: a database is extracted once) -------------
     def save(self, path) -> None:
         """One .npz: ASCII residues + offsets + type/BGC ids + the identity tables."""

@@ -11,12 +11,15 @@ from __future__ import annotations
 
 from .cbind import ALPHABET, BLOSUM62
 
-_SUB = {(a, b): float(BLOSUM62[i, j]) for i, a in enumerate(ALPHABET) for j, b in enumerate(ALPHABET)}
+_SUB62 = {(a, b): float(BLOSUM62[i, j]) for i, a in enumerate(ALPHABET) for j, b in enumerate(ALPHABET)}
 _NEG = float("-inf")
 
 
 def score(a: str, b: str, mode: str = "local", open_gap_score: float = -12.0,
-          extend_gap_score: float = -1.0) -> float:
+          extend_gap_score: float = -1.0, sub=None) -> float:
+    """``sub``: optional 24x24 matrix in ALPHABET order (default BLOSUM62)."""
+    _SUB = _SUB62 if sub is None else \
+        {(x, y): float(sub[i][j]) for i, x in enumerate(ALPHABET) for j, y in enumerate(ALPHABET)}
     if not a or not b:
         raise ValueError("sequence has zero length")
     for ch in a + b:

@@ -46,6 +46,15 @@ class FakeCollection:
         self.bgcs = {}
         self.name = ""
 
+    @classmethod
+    def from_file(cls, collection_file):         # BGClib/BGClib.py:758-777
+        import pickle
+        assert collection_file.is_file()
+        with open(collection_file, "rb") as dc:
+            data = pickle.load(dc)
+        assert isinstance(data, cls)
+        return data
+
 
 class FakeProteinCollection:
     def __init__(self):

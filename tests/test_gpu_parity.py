@@ -106,6 +106,92 @@ def test_protein_length_queries_stay_on_the_packed_kernel(mode):
     assert (res.scores == oracle.all_pairs(seqs, mode=cm)).all()
 
 
+def test_literature_known_answers():
+    """The published worked examples of tests/literature.py through the C ABI (custom matrices,
+    linear and affine gaps, both modes), scores and — for Smith & Waterman's 1981 figure — the
+    alignment coordinates."""
+    import literature
+    from bgclib_b200 import domain_pair_stats
+    for name, a, b, mode, matrix, o, e, want, source in literature.CASES:
+        res = domain_pair_scores([a, b], mode=mode, matrix=matrix, open_gap_score=o, extend_gap_score=e)
+        assert res.scores[0, 1] == want and res.scores[1, 0] == want, (name, source)
+    a, b = literature.CASES[2][1], literature.CASES[2][2]
+    st = domain_pair_stats([a, b], np.array([[0, 1]]), mode="local", matrix=literature.SW1981,
+                           open_gap_score=-4, extend_gap_score=-1).stats[0]
+    assert {k: int(st[k]) for k in st.dtype.names} == literature.SW1981_ALIGNMENT
+
+
+def test_long_queries_against_a_persistent_database():
+    """Queries beyond the packed kernel's reach (> 2048 residues) and a global-mode int16 overflow
+    against a PackedDatabase: the 32-bit fallback list must hold every query x database pair
+    although the database sorts in FRONT of its queries."""
+    from bgclib_b200 import PackedDatabase
+    rng = np.random.default_rng(41)
+    base = _rand(rng, 2700)
+    db_seqs = [base[:100], base[50:170], base[:150], _rand(rng, 200), base[400:620], base[:300]]
+    q_seqs = [base[:2500], base[60:2660], base[100:400]]
+    db = PackedDatabase(db_seqs)
+    for mode, cm in (("local", oracle.MODE_LOCAL), ("global", oracle.MODE_GLOBAL)):
+        dps = domain_pair_scores(q_seqs, database=db, mode=mode)
+        assert dps.plan["n_fallback32"] >= 1
+        full = oracle.all_pairs(q_seqs + db_seqs, mode=cm)
+        assert (dps.scores == full[:3, 3:]).all(), mode
+    # the fused similarity on the same plan shape (rowbest of the long queries must not stay 0)
+    from bgclib_b200.extract import DomainBatch, DomainRecord
+
+    def as_batch(seqs, tag):
+        recs = [DomainRecord(i, f"{tag}{i // 2}", f"p{i}", "d", "KS", 0, len(s), len(s)) for i, s in enumerate(seqs)]
+        ids = sorted({r.bgc_id for r in recs})
+        return DomainBatch(list(seqs), recs, ids, np.asarray([ids.index(r.bgc_id) for r in recs], np.int32),
+                           ["KS"], np.zeros(len(seqs), np.int32))
+    qb, dbb = as_batch(q_seqs, "q"), as_batch(db_seqs, "d")
+    got = bgc_similarity(qb, database=PackedDatabase(dbb))
+    want = bgc_similarity(qb, database=dbb)
+    assert (got.best == want.best).all() and (got.best_db == want.best_db).all() and (got.sim == want.sim).all()
+    assert (got.best > 0).all()
+    # oracle statement of the query -> database direction
+    sc = oracle.all_pairs(q_seqs + db_seqs)
+    for a in range(len(qb.bgc_ids)):
+        for b in range(len(dbb.bgc_ids)):
+            rows = [i for i in range(3) if qb.bgc_of_seq[i] == a]
+            cols = [3 + j for j in range(6) if dbb.bgc_of_seq[j] == b]
+            assert got.best[a, b] == sum(max(sc[i, j] for j in cols) for i in rows)
+
+
+def test_int16_guard_sees_the_longest_subject_of_a_mixed_type_tile():
+    """Types packed, every pair planned (domain_pair_scores against a PackedDatabase): a tile
+    crosses type runs, so its last subject is not its longest.  A 30000-residue subject in global
+    mode leaves int16 and has to take the 32-bit kernel."""
+    from bgclib_b200 import PackedDatabase
+    from bgclib_b200.extract import DomainBatch, DomainRecord
+    rng = np.random.default_rng(43)
+    seqs = [_rand(rng, 100), _rand(rng, 110), _rand(rng, 30000), _rand(rng, 50)]
+    types = ["A", "A", "A", "T"]
+    recs = [DomainRecord(i, f"b{i}", f"p{i}", "d", t, 0, len(s), len(s)) for i, (s, t) in enumerate(zip(seqs, types))]
+    dbb = DomainBatch(seqs, recs, [f"b{i}" for i in range(4)], np.arange(4, dtype=np.int32), ["A", "T"],
+                      np.asarray([0, 0, 0, 1], np.int32))
+    q = [_rand(rng, 105), _rand(rng, 95)]
+    for mode, cm in (("local", oracle.MODE_LOCAL), ("global", oracle.MODE_GLOBAL)):
+        dps = domain_pair_scores(q, database=PackedDatabase(dbb), mode=mode)
+        want = oracle.pair_list(q + seqs, np.repeat([0, 1], 4), np.tile([2, 3, 4, 5], 2), mode=cm).reshape(2, 4)
+        assert (dps.scores == want).all(), mode
+
+
+def test_rejected_query_sets_leave_the_database_usable():
+    """Every way a query set can be refused (empty sequence, too long, illegal letter) leaves the
+    PackedDatabase ready for the next call."""
+    from bgclib_b200 import PackedDatabase
+    rng = np.random.default_rng(44)
+    db_seqs = [_rand(rng, n) for n in (80, 120, 200)]
+    db = PackedDatabase(db_seqs)
+    q = [_rand(rng, 90), _rand(rng, 150)]
+    want = oracle.all_pairs(q + db_seqs)[:2, 2:]
+    for bad in ([q[0], ""], [q[0], "A" * 70000], [q[0], "ACDUFG"]):
+        with pytest.raises(ValueError):      # straight at the C ABI (extract() would drop the empty one)
+            db.engine.pack_append(bad)
+        assert (domain_pair_scores(q, database=db).scores == want).all()
+
+
 def test_pair_list_32bit_kernel():
     rng = np.random.default_rng(6)
     seqs = _related(rng, 3, 4, 100, 700)
@@ -468,6 +554,46 @@ def test_cli_end_to_end(tmp_path, ks_records, af293):
     assert (dmat == 1.0 - want).all() and (np.diag(dmat) == 0).all()
     # query-vs-database through the CLI
     assert cli.main(["--fasta", str(fa), "--db-fasta", str(fa), "--out", str(tmp_path / "x")]) == 0
+
+
+def test_cli_bgccase_bgclist_comparative(tmp_path, af293, ks_records, monkeypatch):
+    """--comparative on .bgccase pickles (BGClib/BGClib.py:758-777) with a --bgclist order, on the
+    GPU.  The reference package does not exist on the GPU box, so a stand-in module named BGClib
+    with the same class surface (tests/fakes.py) is what the pickles load through;
+    tests/test_reference_objects.py runs the loader on pickles of the REAL classes."""
+    import pickle
+    import sys
+    import types
+    import fakes
+    from bgclib_b200 import cli
+    mod = types.ModuleType("BGClib")
+    mod.BGCCollection = fakes.FakeCollection
+    monkeypatch.setitem(sys.modules, "BGClib", mod)
+    col = _af293_collection(af293, ks_records)
+    ids = list(col.bgcs)
+    q, d = fakes.FakeCollection(), fakes.FakeCollection()
+    for k, b in enumerate(ids):
+        (q if k % 3 == 0 else d).bgcs[b] = col.bgcs[b]
+    for name, c in (("q", q), ("d", d), ("all", col)):
+        with open(tmp_path / f"{name}.bgccase", "wb") as f:
+            pickle.dump(c, f)
+    order = [b for b in reversed(ids) if len(extract(col.bgcs[b])) > 0][:9]
+    (tmp_path / "order.tsv").write_text("".join(f"{b}\tprot\tnote\n" for b in order))
+    assert cli.main(["--comparative", "--bgccase", str(tmp_path / "all.bgccase"), "--bgclist",
+                     str(tmp_path / "order.tsv"), "--out", str(tmp_path / "o")]) == 0
+    rows = (tmp_path / "o.bgc_similarity.tsv").read_text().splitlines()
+    assert rows[0].split("\t")[1:] == order and [r.split("\t")[0] for r in rows[1:]] == order
+    sim = np.array([[float(x) for x in r.split("\t")[1:]] for r in rows[1:]])
+    sub = extract(col).select_bgcs(order)
+    want, _, _, _ = oracle.bgc_similarity_np(oracle.all_pairs(sub.sequences), sub.bgc_of_seq, sub.type_of_seq, len(order))
+    assert (sim == want).all()
+    # query pickle against database pickle
+    assert cli.main(["--comparative", "--bgccase", str(tmp_path / "q.bgccase"), "--db-bgccase",
+                     str(tmp_path / "d.bgccase"), "--out", str(tmp_path / "x")]) == 0
+    rows = (tmp_path / "x.bgc_similarity.tsv").read_text().splitlines()
+    got = np.array([[float(x) for x in r.split("\t")[1:]] for r in rows[1:]])
+    ref_res = bgc_similarity(q, database=d)
+    assert rows[0].split("\t")[1:] == ref_res.db_bgc_ids and (got == ref_res.sim).all()
 
 
 # ---- K7: alignment statistics without traceback --------------------------------------------

@@ -105,6 +105,18 @@ def test_planner_balance_and_variants():
     # global mode: a huge gap-extension penalty leaves int16 -> fallback
     _, info_g = plan_host(np.array([400, 420], np.int32), mode=1, open_gap=-40, extend_gap=-40)
     assert info_g["n_fallback32"] == info_g["n_tiles"]
+    # the int16 guard looks at the LONGEST subject of a tile, not at its last one: with types packed
+    # but all pairs planned, a tile crosses type runs and its last subject can be short
+    lens4, types4 = np.array([100, 110, 30000, 50], np.int32), np.array([0, 0, 0, 1], np.int32)
+    tiles, _ = plan_host(lens4, types4, same_type_only=False, mode=1)
+    for t in tiles:
+        if t["s_begin"] <= 2 < t["s_end"]:
+            assert t["variant"] == 0, "a 30000-residue subject in global mode must take the 32-bit kernel"
+    # a persistent database in front of two queries beyond the packed kernel's reach: the cross
+    # tiles fall back to the 32-bit kernel and still account for every query x database pair
+    lens_db = np.array([100, 120, 150, 200, 220, 300, 2500, 2600], np.int32)
+    tiles, info = plan_host(lens_db, cross_only=2, n_db_first=6)
+    assert info["n_fallback32"] >= 1 and info["total_pairs"] == 2 * 6 + 2
 
 
 def test_extract_from_collection():

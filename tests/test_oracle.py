@@ -36,6 +36,23 @@ def test_oracle_reproduces_app_b(ks_records, key):
     assert hashlib.sha256(m.astype("<i4").tobytes()).hexdigest() == sha
 
 
+def test_literature_known_answers():
+    """Published worked examples (tests/literature.py cites page and figure) through the matrix=
+    path of all three oracle formulations: C H/E/F, C 3-state, pure-Python 3-state with floats."""
+    import literature
+    for name, a, b, mode, matrix, o, e, want, source in literature.CASES:
+        sub = oracle.BLOSUM62 if isinstance(matrix, str) else matrix
+        cm = oracle.MODE_LOCAL if mode == "local" else oracle.MODE_GLOBAL
+        assert oracle.score(a, b, mode=cm, sub=sub, open_gap=o, extend_gap=e) == want, (name, source)
+        assert oracle.score(b, a, mode=cm, sub=sub, open_gap=o, extend_gap=e) == want, (name, source)
+        assert oracle.score_3state(a, b, mode=cm, sub=sub, open_gap=o, extend_gap=e) == want, (name, source)
+        assert gotoh_py.score(a, b, mode, o, e, sub=sub) == float(want), (name, source)
+    a, b = literature.CASES[2][1], literature.CASES[2][2]
+    st = oracle.stats_list([a, b], [0], [1], mode=oracle.MODE_LOCAL, sub=literature.SW1981, open_gap=-4,
+                           extend_gap=-1)[0]
+    assert {k: int(st[k]) for k in st.dtype.names} == literature.SW1981_ALIGNMENT
+
+
 def test_committed_golden_matches_app_b(ks_golden):
     for key, (sha, row0, _) in APP_B.items():
         assert ks_golden[key]["sha256_int32_le"] == sha

@@ -70,3 +70,82 @@ def test_attach_adds_methods_without_state(ref):
     col = cls()
     pickle.dumps(col)
 
+
+
+def _real_collection(ref, ks_records, lo, hi, tag=""):
+    """A BGCCollection of the REAL reference classes: one rPKS protein per KS record, the KS
+    domain embedded between linkers, BGC = the record's BGC."""
+    col = ref.BGCCollection()
+    for r in ks_records[lo:hi]:
+        bid = r["bgc"] + tag
+        bgc = col.bgcs.get(bid)
+        if bgc is None:
+            bgc = ref.BGC()
+            bgc.identifier = bid
+            col.bgcs[bid] = bgc
+        p = ref.BGCProtein()
+        p.identifier = r["protein_identifier"] + tag + f"#{len(bgc.protein_list)}"
+        p.parent_cluster_id = bid
+        p.sequence = "MA" + r["sequence"] + "GK"
+        p.domain_list.append(ref.BGCDomain(p, "ketoacyl-synt", "PF00109.27", "", "", 2, 2 + len(r["sequence"]),
+                                           0, 250, 253, 300.0, 1e-90, ""))
+        bgc.protein_list.append(p)
+        bgc.proteins[p.identifier] = p
+        bgc.CBPcontent.setdefault("rPKS", []).append(p)
+    return col
+
+
+def test_cli_reads_bgccase_pickles_of_the_real_classes(ref, ks_records, tmp_path, monkeypatch):
+    """--bgccase / --db-bgccase / --bgclist / --comparative on pickles written from the real
+    BGCCollection (BGClib/BGClib.py:758-777).  No GPU here: the similarity call behind the CLI is
+    replaced by the oracle's statement of it, so what is checked is the loader, the BGC list
+    filter and order, and the tables written."""
+    import numpy as np
+    import oracle
+    from bgclib_b200 import api, cli, extract
+    col, dbc = _real_collection(ref, ks_records, 0, 8), _real_collection(ref, ks_records, 8, 15, tag="_db")
+    case, dbcase = tmp_path / "q.bgccase", tmp_path / "db.bgccase"
+    for path, c in ((case, col), (dbcase, dbc)):
+        with open(path, "wb") as f:
+            pickle.dump(c, f)
+    alias_tsv = tmp_path / "alias.tsv"
+    alias_tsv.write_text("# comment\nketoacyl-synt\tKS\n")
+    alias = cli.read_alias_tsv(alias_tsv)
+    got = cli.batch_from_bgccase(case, alias)
+    want = extract(col, alias=alias)
+    assert got.sequences == want.sequences == [r["sequence"] for r in ks_records[:8]]
+    assert got.bgc_ids == want.bgc_ids and [r.type_key for r in got.records] == ["KS"] * 8
+
+    seen = {}
+
+    def oracle_similarity(batch, database=None, same_type_only=True, **kw):
+        seen["batch"], seen["db"] = batch, database
+        seqs = batch.sequences + (database.sequences if database is not None else [])
+        Bq = len(batch.bgc_ids)
+        bgcs = np.concatenate([batch.bgc_of_seq, database.bgc_of_seq + Bq]) if database is not None else batch.bgc_of_seq
+        B = Bq + (len(database.bgc_ids) if database is not None else 0)
+        sim, best, selfs, _ = oracle.bgc_similarity_np(oracle.all_pairs(seqs), bgcs, np.zeros(len(seqs), int), B)
+        if database is None:
+            return api.BGCSimilarity(sim, best, selfs, list(batch.bgc_ids), batch.records, {"total_pairs": 0})
+        return api.BGCSimilarity(sim[:Bq, Bq:], best[:Bq, Bq:], selfs[:Bq], list(batch.bgc_ids), batch.records,
+                                 {"total_pairs": 0}, list(database.bgc_ids), selfs[Bq:], best[Bq:, :Bq])
+    monkeypatch.setattr(api, "bgc_similarity", oracle_similarity)
+
+    ids = list(col.bgcs)
+    order = [ids[2], ids[0], "not_a_bgc", ids[1]]
+    lst = tmp_path / "order.tsv"
+    lst.write_text("# bgc\tprotein\tcomment\n" + "".join(f"{b}\t\tx\n" for b in order) + "\n")
+    out = tmp_path / "res"
+    assert cli.main(["--comparative", "--bgccase", str(case), "--alias-tsv", str(alias_tsv), "--bgclist", str(lst),
+                     "--out", str(out)]) == 0
+    rows = (tmp_path / "res.bgc_similarity.tsv").read_text().splitlines()
+    assert rows[0].split("\t")[1:] == [ids[2], ids[0], ids[1]] == [r.split("\t")[0] for r in rows[1:]]
+    assert seen["batch"].bgc_ids == [ids[2], ids[0], ids[1]]
+    assert all(r.bgc_id in (ids[2], ids[0], ids[1]) for r in seen["batch"].records)
+    assert float(rows[1].split("\t")[1]) == 1.0
+    # query pickle against database pickle
+    assert cli.main(["--comparative", "--bgccase", str(case), "--db-bgccase", str(dbcase), "--alias-tsv",
+                     str(alias_tsv), "--out", str(tmp_path / "x")]) == 0
+    rows = (tmp_path / "x.bgc_similarity.tsv").read_text().splitlines()
+    assert rows[0].split("\t")[1:] == list(dbc.bgcs) and [r.split("\t")[0] for r in rows[1:]] == ids
+    assert seen["db"].sequences == [r["sequence"] for r in ks_records[8:15]]
