@@ -255,10 +255,9 @@ def bgc_similarity(source, *, database=None, matrix="BLOSUM62", open_gap_score=-
     rounds = max(1, int(rounds))
     ckpt = _Checkpoint(checkpoint, rank, batch, bgc_of, B, matrix, open_gap_score, extend_gap_score,
                        same_type_only, rounds, world) if checkpoint is not None else None
-    done = set()
+    done, plan = set(), None
     if ckpt is not None:
-        done = ckpt.load_into(rowbest, selfsc)
-    plan = None
+        done, plan = ckpt.load_into(rowbest, selfsc)    # plan statistics of the finished rounds ride along
     for r in range(rounds):
         if r in done:                       # finished before the interruption: nothing to plan or score
             continue
@@ -268,11 +267,9 @@ def bgc_similarity(source, *, database=None, matrix="BLOSUM62", open_gap_score=-
         eng.score(rowbest=rowbest, selfsc=selfsc, type_check=False)
         done.add(r)
         if ckpt is not None:
-            ckpt.save(rowbest, selfsc, done)
+            ckpt.save(rowbest, selfsc, done, plan)
         if _stop_after_rounds is not None and len(done) >= _stop_after_rounds:
             raise KeyboardInterrupt(f"stopped after {len(done)} of {rounds} rounds (test hook)")
-    if plan is None:                        # every round came from the checkpoint
-        plan = {"resumed_rounds": len(done)}
     if dist is not None:
         dist.all_reduce(rowbest, op=dist.ReduceOp.MAX)
         dist.all_reduce(selfsc, op=dist.ReduceOp.MAX)
@@ -306,19 +303,21 @@ class _Checkpoint:
 
     def load_into(self, rowbest, selfsc):
         if not self.path.exists():
-            return set()
+            return set(), None
         z = np.load(self.path, allow_pickle=False)
         if str(z["tag"]) != self.tag or z["rowbest"].shape != tuple(rowbest.shape):
-            return set()                      # different input or parameters: start over
+            return set(), None                # different input or parameters: start over
+        import json
         import torch
         rowbest.copy_(torch.from_numpy(z["rowbest"]))
         selfsc.copy_(torch.from_numpy(z["selfsc"]))
-        return set(int(r) for r in z["done"])
+        return set(int(r) for r in z["done"]), json.loads(str(z["plan"]))
 
-    def save(self, rowbest, selfsc, done):
+    def save(self, rowbest, selfsc, done, plan):
+        import json
         tmp = self.path.with_suffix(".tmp.npz")
         np.savez(tmp, tag=np.asarray(self.tag), rowbest=rowbest.cpu().numpy(), selfsc=selfsc.cpu().numpy(),
-                 done=np.asarray(sorted(done), dtype=np.int64))
+                 done=np.asarray(sorted(done), dtype=np.int64), plan=np.asarray(json.dumps(plan)))
         tmp.replace(self.path)
 
 

@@ -30,11 +30,17 @@ UNITS = [("bgca_api.o", "bgca_api.cu", []),
          ("pack_reduce.o", "pack_reduce.cu", []),
          ("stats.o", "stats.cu", []),
          ("dpx_probe.o", "dpx_probe.cu", [])]
-for g in (4, 8, 16, 32):
+for g in (1, 2, 4, 8, 16, 32):
     for m in (0, 1):
         for pr in (0, 1, 2):
             UNITS.append((f"dp_g{g}_m{m}_p{pr}.o", "dp_inst.cu",
                           [f"-DBGCA_INST_G={g}", f"-DBGCA_INST_MODE={m}", f"-DBGCA_INST_PRESET={pr}"]))
+
+
+for m in (0, 1):                 # multi-pass whole-warp instantiations (queries > 1024 residues)
+    for pr in (0, 1, 2):
+        UNITS.append((f"dp_mp_m{m}_p{pr}.o", "dp_inst.cu",
+                      ["-DBGCA_INST_G=32", "-DBGCA_INST_MP=1", f"-DBGCA_INST_MODE={m}", f"-DBGCA_INST_PRESET={pr}"]))
 
 
 def _sources_mtime() -> float:

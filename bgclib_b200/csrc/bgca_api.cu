@@ -43,6 +43,7 @@ const VariantDesc kVariants[] = {
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr int kSubjectsPerGroup = 16;
 constexpr uint64_t kPackedHeader = 64;    // bytes of TOK_IDLE (25) in front of the first sequence
+constexpr int kMpTokensPerGroup = 32768;  // multi-pass tiles: target length of one group's subject stream
 
 // Relative issue cost per subject column with variant (G,K): (instructions per step:
 // 5.5 per row + ~21 of step overhead + one LDS.128 per 4 rows) x (share of the warp one
@@ -52,6 +53,13 @@ double variant_cost(int G, int K, int /*Lq*/)
     return (5.5 * K + 21.0 + (K + 3) / 4) * (double)G;
 }
 
+// BGCA_MIN_G=n keeps the planner off group widths below n (tuning aid, e.g. 4 = the round-1 set).
+int min_group_width()
+{
+    const char *s = std::getenv("BGCA_MIN_G");
+    return s ? std::atoi(s) : 1;
+}
+
 // BGCA_FORCE_G=4|8|16|32 restricts the planner to one group width (tuning aid).
 int forced_group_width()
 {
@@ -59,18 +67,26 @@ int forced_group_width()
     return s ? std::atoi(s) : 0;
 }
 
-// n_subjects: subjects the query pair meets in its block.  G = 4 runs 64 subject streams per CTA
-// and is only offered when there are enough subjects to keep them busy.
+// n_subjects: subjects the query pair meets in its block.  G = 4 / 2 / 1 run 64 / 128 / 256 subject
+// streams per CTA and are only offered when there are enough subjects to keep them busy.
 int pick_variant(int Lq, int mode, int n_subjects = 1 << 30)
 {
     int best = 0;
     double best_cost = 0.0;
     const int force_g = forced_group_width();
+    const int min_g = min_group_width();
     (void)mode;   // local and global kernels have the same register budget
+    if (Lq > BGCA_ONE_PASS_ROWS) {
+        // multi-pass whole-warp sweep: the fewest passes of <= 1024 rows, rows spread evenly
+        const int npass = (Lq + BGCA_ONE_PASS_ROWS - 1) / BGCA_ONE_PASS_ROWS;
+        const int K = (Lq + 32 * npass - 1) / (32 * npass);      // 17..32
+        return BGCA_VARIANT_MP | BGCA_VARIANT_ID(32, K);
+    }
     for (int v = 0; v < kNumVariants; ++v) {
         const int G = kVariants[v].G, K = kVariants[v].K;
         if (G * K < Lq) continue;
-        if (G == 4 && force_g != 4 && n_subjects < 4 * (CTA_THREADS / 4)) continue;
+        if (G < min_g) continue;
+        if (G <= 4 && force_g != G && n_subjects < 4 * (CTA_THREADS / G)) continue;
         if (force_g && G != force_g && force_g * 32 >= Lq) continue;
         const double c = variant_cost(G, K, Lq);
         if (!best || c < best_cost) {
@@ -215,11 +231,14 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
         if (S <= 0) return;
         if (counting) { visits += S; return; }
         const int variant = pick_variant(Lq, mode, S);
-        const int G = variant >> 8;
+        const int G = (variant >> 8) & 0xFF;
         // subjects per tile: ~spg per alignment group (= subject stream) of the CTA,
         // split evenly over the row and rounded up to a whole number per group
         const int ngroups = variant ? CTA_THREADS / G : 16;
-        const int s_max = ngroups * spg;
+        int spg_row = spg;
+        if (variant & BGCA_VARIANT_MP)    // bounds the line of parked rows a group keeps between passes
+            spg_row = std::max(1, std::min(spg, kMpTokensPerGroup / (max_len_in(sub0, te) + 1)));
+        const int s_max = ngroups * spg_row;
         const int nchunks = (S + s_max - 1) / s_max;
         int chunk = (S + nchunks - 1) / nchunks;
         chunk = (chunk + ngroups - 1) / ngroups * ngroups;
@@ -407,7 +426,7 @@ struct bgca_engine {
     DevBuf<uint32_t> d_seq_off;
     DevBuf<unsigned long long> d_err;
     DevBuf<bgca_tile> d_tiles;
-    DevBuf<int2> d_scratch;
+    DevBuf<int2> d_scratch, d_mp_scratch;
     DevBuf<uint4> d_scratch_st;
     DevBuf<int32_t> d_scores_host_call;   // bgca_score_all_host's n x n staging matrix
     // plan
@@ -474,7 +493,7 @@ int bgca_destroy(bgca_engine *e)
     e->d_ascii.release(); e->d_codes.release(); e->d_offsets_orig.release(); e->d_order.release();
     e->d_len.release(); e->d_type.release(); e->d_bgc.release(); e->d_bgc_start.release();
     e->d_bgc_doms.release(); e->d_counters.release(); e->d_pq.release(); e->d_ps.release();
-    e->d_seq_off.release(); e->d_err.release(); e->d_tiles.release(); e->d_scratch.release(); e->d_scratch_st.release(); e->d_scores_host_call.release();
+    e->d_seq_off.release(); e->d_err.release(); e->d_tiles.release(); e->d_scratch.release(); e->d_mp_scratch.release(); e->d_scratch_st.release(); e->d_scores_host_call.release();
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->evp0) cudaEventDestroy(e->evp0);
@@ -932,6 +951,29 @@ try {
         runs.push_back({i, j});
         i = j;
     }
+    // multi-pass runs: one line of parked (Ho, F) pairs per CTA and group, as long as the longest
+    // subject stream a group of any such tile reads (+ wind-up and the two-step prefetch); runs
+    // execute concurrently on the side streams, so each gets its own lines
+    int mp_stride = 0;
+    size_t mp_runs = 0, mp_lines_used = 0;
+    for (const auto &run : runs) {
+        if (!(e->tiles[run.first].variant & BGCA_VARIANT_MP)) continue;
+        ++mp_runs;
+        const int ng = CTA_THREADS / 32;
+        for (size_t i = run.first; i < run.second; ++i) {
+            const bgca_tile &T = e->tiles[i];
+            for (int g = 0; g < ng; ++g) {
+                int tokens = 0;
+                for (int s = T.s_begin + g; s < T.s_end; s += ng) tokens += e->len[s] + 1;
+                mp_stride = std::max(mp_stride, tokens);
+            }
+        }
+    }
+    if (mp_runs) {
+        mp_stride = (mp_stride + 32 + 2 + 15) & ~15;
+        CUDA_TRY(e->d_mp_scratch.reserve(mp_runs * (size_t)pair16_mp_max_grid(e->n_sm) * (CTA_THREADS / 32) *
+                                         (size_t)mp_stride));
+    }
     CUDA_TRY(e->d_counters.reserve(runs.size() + 1));
     CUDA_TRY(cudaMemsetAsync(e->d_counters.p, 0, sizeof(int32_t) * (runs.size() + 1), st));
     CUDA_TRY(cudaEventRecord(e->ev0, st));
@@ -970,12 +1012,17 @@ try {
         p.tiles = e->d_tiles.p + b;
         p.n_tiles = (int32_t)(en - b);
         p.tile_counter = e->d_counters.p + r;
-        const int G = variant >> 8, K = variant & 0xFF;
+        const int G = (variant >> 8) & 0xFF, K = variant & 0xFF;
+        const bool multipass = (variant & BGCA_VARIANT_MP) != 0;
         cudaError_t err = cudaErrorInvalidValue;
         int grid = 0;
         const bool local = e->mode == BGCA_MODE_LOCAL;
         // [G index][mode][gap preset]; preset 0 takes the gap scores at run time
-        static const Pair16Launcher table[4][2][3] = {
+        static const Pair16Launcher table[6][2][3] = {
+            {{launch_pair16_g1_m0_p0, launch_pair16_g1_m0_p1, launch_pair16_g1_m0_p2},
+             {launch_pair16_g1_m1_p0, launch_pair16_g1_m1_p1, launch_pair16_g1_m1_p2}},
+            {{launch_pair16_g2_m0_p0, launch_pair16_g2_m0_p1, launch_pair16_g2_m0_p2},
+             {launch_pair16_g2_m1_p0, launch_pair16_g2_m1_p1, launch_pair16_g2_m1_p2}},
             {{launch_pair16_g4_m0_p0, launch_pair16_g4_m0_p1, launch_pair16_g4_m0_p2},
              {launch_pair16_g4_m1_p0, launch_pair16_g4_m1_p1, launch_pair16_g4_m1_p2}},
             {{launch_pair16_g8_m0_p0, launch_pair16_g8_m0_p1, launch_pair16_g8_m0_p2},
@@ -984,7 +1031,7 @@ try {
              {launch_pair16_g16_m1_p0, launch_pair16_g16_m1_p1, launch_pair16_g16_m1_p2}},
             {{launch_pair16_g32_m0_p0, launch_pair16_g32_m0_p1, launch_pair16_g32_m0_p2},
              {launch_pair16_g32_m1_p0, launch_pair16_g32_m1_p1, launch_pair16_g32_m1_p2}}};
-        const int gi = (G == 4) ? 0 : (G == 8) ? 1 : (G == 16) ? 2 : (G == 32) ? 3 : -1;
+        const int gi = (G == 1) ? 0 : (G == 2) ? 1 : (G == 4) ? 2 : (G == 8) ? 3 : (G == 16) ? 4 : (G == 32) ? 5 : -1;
         int preset = 0;
         if (e->open == -12 && e->extend == -1) preset = 1;
         else if (e->open == -11 && e->extend == -1) preset = 2;
@@ -999,7 +1046,15 @@ try {
                 n_side_used = si + 1;
             }
         }
-        if (gi >= 0) err = table[gi][local ? 0 : 1][preset](K, p, e->n_sm, ks, &grid);
+        if (multipass) {
+            static const Pair16Launcher mp_table[2][3] = {
+                {launch_pair16_mp_m0_p0, launch_pair16_mp_m0_p1, launch_pair16_mp_m0_p2},
+                {launch_pair16_mp_m1_p0, launch_pair16_mp_m1_p1, launch_pair16_mp_m1_p2}};
+            p.mp_scratch = e->d_mp_scratch.p + mp_lines_used * (size_t)mp_stride;
+            p.mp_stride = mp_stride;
+            mp_lines_used += (size_t)pair16_mp_max_grid(e->n_sm) * (CTA_THREADS / 32);
+            err = mp_table[local ? 0 : 1][preset](K, p, e->n_sm, ks, &grid);
+        } else if (gi >= 0) err = table[gi][local ? 0 : 1][preset](K, p, e->n_sm, ks, &grid);
         if (err != cudaSuccess)
             return fail(BGCA_ERR_CUDA, std::string("DP kernel launch (G=") + std::to_string(G) + ",K=" +
                                            std::to_string(K) + "): " + cudaGetErrorString(err));

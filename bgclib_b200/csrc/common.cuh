@@ -37,6 +37,11 @@ struct ScoreParams {
     // queries, the rest the database.  cross_q0 = 0 for a batch packed [queries | database] in one
     // call, = n_database when queries were appended behind a persistent database.
     int32_t cross_nq, cross_q0;
+    // multi-pass sweep of queries longer than one pass (G*K rows): per CTA and alignment group a
+    // line of mp_stride (Ho, F) pairs — the bottom row of a pass, one entry per stream position —
+    // parked in L2/HBM for the next pass to take as its top boundary
+    int2 *mp_scratch;
+    int32_t mp_stride;
     int8_t sub[NSYM * NSYM];
 };
 

@@ -28,6 +28,15 @@
 // every LDS.128 of a quarter-warp hit 8 distinct 16-byte bank groups whatever
 // letter each lane looks up (row stride is a multiple of 128 B).
 //
+// Multi-pass (MP = 1, G = 32).  A query pair longer than one pass (32*K rows) is swept in
+// ceil(L / (32*K)) passes over the same subject stream: the last lane parks the (Ho, F) it hands
+// on — the bottom row of the pass, one pair per stream position — in an L2-resident scratch
+// line, and lane 0 of the next pass takes its top boundary from there (prefetched two steps
+// ahead like the tokens) instead of the constant boundary row.  Local best scores are carried
+// from pass to pass per subject; global scores are emitted by the pass that owns the last row.
+// Any query length the packer accepts runs this way at the occupancy of the K <= 32 variants
+// (two CTAs per SM), so the 32-bit kernel only serves pairs whose scores leave int16.
+//
 // Per cell pair ("next-T" form).  The per-row state is not H but what the NEXT
 // column needs from it: Tn[k] = Ho[k-1] + (s_next - open) (the diagonal term,
 // built with the profile row of the NEXT token, which is prefetched two steps
@@ -76,8 +85,21 @@ struct Pair16Cfg {
     static constexpr int ROW_BYTES = CH * G * 16;   // one profile row (multiple of 128 B)
     static constexpr int NGROUPS = CTA_THREADS / G; // alignment groups (subject streams) per CTA
     static constexpr int PROF_BYTES = PROF_ROWS * ROW_BYTES;
-    static constexpr int BEST_BYTES = NGROUPS * 32 * 2 * 4;   // per group: ring of 32 (lo, hi) slots
+    // per group a ring of (lo, hi) best slots: lane 0 can run at most G-1 subjects ahead of the
+    // last lane (one-residue subjects), so G slots never collide
+    static constexpr int RING = G;
+    static constexpr int BEST_BYTES = NGROUPS * RING * 2 * 4;
+    // Groups that share a warp keep their subject streams in step (G <= 4: 8+ streams per warp,
+    // short subjects): after a subject a group idles until the longest subject of the warp's
+    // batch has ended, so the cold boundary path runs once per batch and warp instead of once per
+    // group — unsynchronised, a 20-residue batch spends more issue slots in boundary code than in
+    // DP cells.
+    static constexpr bool ALIGN_STREAMS = (G <= 4);
     static constexpr int SMEM_BYTES = PROF_BYTES + BEST_BYTES + 2 * LPAD + NSYM * NSYM + 16;
+    // multi-pass: best-so-far of every subject of the tile, carried between passes
+    static constexpr int MP_MAX_SUBJECTS = 64;                 // per group and tile (planner: spg <= 64)
+    static constexpr int MP_BEST_BYTES = NGROUPS * MP_MAX_SUBJECTS * 2 * 4;
+    static constexpr int SMEM_BYTES_MP = SMEM_BYTES + MP_BEST_BYTES;
     // registers: 2K state + 4CH profile + ~24 -> pick CTAs/SM so ptxas has room.
     static constexpr int MIN_CTAS_LOCAL = (K <= 6) ? 5 : (K <= 14) ? 4 : (K <= 18) ? 3 : (K <= 32) ? 2 : 1;
     static constexpr int MIN_CTAS_GLOBAL = (K <= 4) ? 5 : (K <= 9) ? 4 : (K <= 14) ? 3 : (K <= 32) ? 2 : 1;   // a few more live values (boundary walk)
@@ -92,11 +114,12 @@ template <> struct GapPreset<1> { static constexpr int OPEN = -12, EXT = -1; }; 
 template <> struct GapPreset<2> { static constexpr int OPEN = -11, EXT = -1; };   // BLAST "11/1" read as open+extend
 constexpr int NUM_GAP_PRESETS = 3;
 
-template <int G, int K, int MODE, int PRESET>
-__global__ void __launch_bounds__(CTA_THREADS, (MODE == BGCA_MODE_LOCAL ? Pair16Cfg<G, K>::MIN_CTAS_LOCAL
-                                                                         : Pair16Cfg<G, K>::MIN_CTAS_GLOBAL))
+template <int G, int K, int MODE, int PRESET, int MP = 0>
+__global__ void __launch_bounds__(CTA_THREADS, (MP ? 2 : MODE == BGCA_MODE_LOCAL ? Pair16Cfg<G, K>::MIN_CTAS_LOCAL
+                                                                              : Pair16Cfg<G, K>::MIN_CTAS_GLOBAL))
 gotoh_pair16_kernel(const ScoreParams p)
 {
+    static_assert(!MP || G == 32, "the multi-pass sweep is built for whole-warp groups");
     using Cfg = Pair16Cfg<G, K>;
     constexpr int CH = Cfg::CH, LPAD = Cfg::LPAD, NGROUPS = Cfg::NGROUPS;
     constexpr bool LOCAL = (MODE == BGCA_MODE_LOCAL);
@@ -107,6 +130,8 @@ gotoh_pair16_kernel(const ScoreParams p)
     int *sbest = reinterpret_cast<int *>(reinterpret_cast<uint8_t *>(smem_u4) + Cfg::PROF_BYTES);
     uint8_t *qcodes = reinterpret_cast<uint8_t *>(sbest) + Cfg::BEST_BYTES;   // [2][LPAD]
     int8_t *ssub = reinterpret_cast<int8_t *>(qcodes + 2 * LPAD);
+    // [NGROUPS][MP_MAX_SUBJECTS][2], touched only by the last lane of each group
+    int *pbest = reinterpret_cast<int *>(reinterpret_cast<uint8_t *>(smem_u4) + ((Cfg::SMEM_BYTES + 15) & ~15));
     __shared__ int s_tile;
 
     const int tid = threadIdx.x;
@@ -122,7 +147,7 @@ gotoh_pair16_kernel(const ScoreParams p)
     const uint32_t ext2 = PRESET ? cpack2(GapPreset<PRESET>::EXT) : p.ext2;
     const uint32_t open2 = PRESET ? cpack2(GapPreset<PRESET>::OPEN) : p.open2;
     const uint8_t *const idle_ptr = p.codes;            // header of the packed batch: TOK_IDLE bytes
-    int *const my_best = sbest + gid * 64;
+    int *const my_best = sbest + gid * (Cfg::RING * 2);
     // this lane's 16-byte column of the profile, as a 32-bit shared-window address
     const uint32_t prof_lane = (uint32_t)__cvta_generic_to_shared(prof) + (uint32_t)t * 16u;
 
@@ -135,14 +160,25 @@ gotoh_pair16_kernel(const ScoreParams p)
         const int qa = T.qa, qb = T.qb;
         const int La = p.seq_len[qa];
         const int Lb = (qb >= 0) ? p.seq_len[qb] : 0;
+        const int npass = MP ? (max(La, Lb) + LPAD - 1) / LPAD : 1;
+        // this group's line of parked (Ho, F) pairs, indexed by stream position
+        int2 *const mp_line = MP ? p.mp_scratch + ((size_t)blockIdx.x * NGROUPS + gid) * (size_t)p.mp_stride : nullptr;
+
+      for (int pass = 0; pass < npass; ++pass) {
+        const int row0 = pass * LPAD;           // first query row of this pass
+        const int gi0 = row0 + i0;              // first query row of this lane
+        const bool from_park = MP && pass > 0;  // lane 0 takes its top boundary from the parked row
+        const bool park = MP && pass + 1 < npass;
+        if (MP && pass > 0) __syncthreads();    // every warp is done with the profile of the last pass
+                                                // (and its parked row is visible to the whole CTA)
 
         // ---- stage the two queries, then build the pair profile ----------------
         {
-            const uint8_t *ca = p.codes + p.seq_off[qa];
-            const uint8_t *cb = p.codes + p.seq_off[qb >= 0 ? qb : qa];
+            const uint8_t *ca = p.codes + p.seq_off[qa] + row0;
+            const uint8_t *cb = p.codes + p.seq_off[qb >= 0 ? qb : qa] + row0;
             for (int i = tid; i < LPAD; i += CTA_THREADS) {
-                qcodes[i] = (i < La) ? ca[i] : (uint8_t)255;
-                qcodes[LPAD + i] = (i < Lb) ? cb[i] : (uint8_t)255;
+                qcodes[i] = (row0 + i < La) ? ca[i] : (uint8_t)255;
+                qcodes[LPAD + i] = (row0 + i < Lb) ? cb[i] : (uint8_t)255;
             }
         }
         __syncthreads();
@@ -164,8 +200,16 @@ gotoh_pair16_kernel(const ScoreParams p)
         // ---- this group's subject stream ------------------------------------------
         const int s_first = T.s_begin + gid;
         const int n_g = (s_first < T.s_end) ? (T.s_end - s_first + NGROUPS - 1) / NGROUPS : 0;
+        // the subject of the last group of this warp in batch o: the longest of the warp's batch
+        // when lengths ascend (they do inside a type block); any other case only aligns less well
+        const int s_wlast = T.s_begin + (tid | 31) / G;
+        auto stream_len = [&](int o) {          // steps batch o takes in this group's stream
+            const int own = p.seq_len[s_first + o * NGROUPS];
+            if (!Cfg::ALIGN_STREAMS) return own + 1;
+            return max(own, p.seq_len[min(s_wlast + o * NGROUPS, T.s_end - 1)]) + 1;
+        };
         int nsteps = 0;
-        for (int o = t; o < n_g; o += G) nsteps += p.seq_len[s_first + o * NGROUPS] + 1;
+        for (int o = t; o < n_g; o += G) nsteps += stream_len(o);
 #pragma unroll
         for (int off = G / 2; off > 0; off >>= 1) nsteps += __shfl_xor_sync(FULL, nsteps, off);
         nsteps = (n_g > 0) ? nsteps + G - 1 : 0;
@@ -182,11 +226,11 @@ gotoh_pair16_kernel(const ScoreParams p)
         uint32_t h_out = 0, f_out = 0;
         uint32_t top_h = LOCAL ? open2 : pack2(2 * p.open);     // lane 0: Ho[-1][j]
         // column boundary (j = -1) of the row above this lane: Ho[i0-1][-1]
-        const uint32_t hin0 = (LOCAL || t == 0) ? open2 : pack2(2 * p.open + (i0 - 1) * p.extend);
+        const uint32_t hin0 = (LOCAL || gi0 == 0) ? open2 : pack2(2 * p.open + (gi0 - 1) * p.extend);
         // local mode: the top boundary row is constant (Ho = open, F = 0), so lane 0 takes it with
         // one LOP3 per value instead of a compare and two selects per step
-        uint32_t keep_in = (t == 0) ? 0u : 0xFFFFFFFFu;
-        uint32_t top_or = (t == 0) ? open2 : 0u;
+        uint32_t keep_in = (t == 0 && !from_park) ? 0u : 0xFFFFFFFFu;
+        uint32_t top_or = (t == 0 && !from_park) ? open2 : 0u;
         asm volatile("" : "+r"(keep_in), "+r"(top_or));   // opaque: keeps ptxas from turning them back into selects
 
         // start of a subject whose first residue is c0: state for column 0
@@ -201,7 +245,7 @@ gotoh_pair16_kernel(const ScoreParams p)
             // Ho[i0+k][-1], walked down the rows.  The empty asm makes the start value opaque so
             // the K loop-invariant boundary words are rebuilt here (cold path) instead of being
             // hoisted into 2K registers that would stay live across the hot loop.
-            uint32_t col = LOCAL ? open2 : pack2(2 * p.open + i0 * p.extend);
+            uint32_t col = LOCAL ? open2 : pack2(2 * p.open + gi0 * p.extend);
             asm volatile("" : "+r"(col));
             uint32_t above = hin0;
 #pragma unroll
@@ -233,15 +277,28 @@ gotoh_pair16_kernel(const ScoreParams p)
             begin_subject(c);
         }
 
+        // multi-pass: the parked row of the previous pass, two steps ahead of its use (lane 0 only)
+        const bool park_reader = from_park && t == 0;
+        int2 bnd = make_int2(0, 0), bnd1 = make_int2(0, 0);
+        if (park_reader) { bnd = __ldcg(mp_line); bnd1 = __ldcg(mp_line + 1); }
+
         for (int tau = 0; tau < nsteps; ++tau) {
             uint32_t h_in = __shfl_up_sync(FULL, h_out, 1, G);
             uint32_t f_in = __shfl_up_sync(FULL, f_out, 1, G);
             off += 1;
             uint32_t c2 = ldg_token(p.codes + off);
+            int2 bnd2 = make_int2(0, 0);
+            if (MP) {
+                if (park_reader) {              // Ho / F of row row0-1 at this stream position
+                    bnd2 = __ldcg(mp_line + tau + 2);
+                    h_in = (uint32_t)bnd.x;
+                    f_in = (uint32_t)bnd.y;
+                }
+            }
             if (LOCAL) {                        // top boundary row: Ho[-1][j] = open, F[-1][j] = 0
                 h_in = (h_in & keep_in) | top_or;
                 f_in &= keep_in;
-            } else if (t == 0) {                // global: Ho[-1][j] walks down the boundary
+            } else if (t == 0 && !from_park) {  // global: Ho[-1][j] walks down the boundary
                 h_in = top_h;
                 f_in = NEG16x2;
             }
@@ -273,21 +330,34 @@ gotoh_pair16_kernel(const ScoreParams p)
                     h_out = up;
                     f_out = F;
                     if (!LOCAL) top_h = __vadd2(top_h, ext2);
+                    if (MP) {                   // bottom row of this pass, by stream position
+                        if (park && t == G - 1) __stcg(mp_line + (tau - (G - 1)), make_int2((int)up, (int)F));
+                    }
                 }
             } else if (c == TOK_BOUNDARY) {
                 // ================= cold path: the subject just ended ====================
                 const int s = s_first + ord * NGROUPS;
                 if (LOCAL) {
-                    int *slot = my_best + (ord & 31) * 2;
+                    int *slot = my_best + (ord & (Cfg::RING - 1)) * 2;
                     const int lo = (int)(int16_t)(best & 0xFFFFu), hi = (int)(int16_t)(best >> 16);
-                    if (t != G - 1) {
+                    if (G == 1) {               // the lane holds the whole query: nothing to collect
+                        emit_pair(p, qa, s, max(lo, 0));
+                        emit_pair(p, qb, s, max(hi, 0));
+                    } else if (t != G - 1) {
                         if (lo > 0) atomicMax(slot, lo);
                         if (hi > 0) atomicMax(slot + 1, hi);
                     } else {                    // every other lane passed this boundary earlier
-                        const int a = max(lo, atomicExch(slot, 0));
-                        const int b = max(hi, atomicExch(slot + 1, 0));
-                        emit_pair(p, qa, s, a);
-                        emit_pair(p, qb, s, b);
+                        int a = max(lo, atomicExch(slot, 0));
+                        int b = max(hi, atomicExch(slot + 1, 0));
+                        if (MP) {               // best of the earlier passes of this subject
+                            int *pb = pbest + (gid * Cfg::MP_MAX_SUBJECTS + ord) * 2;
+                            if (pass > 0) { a = max(a, pb[0]); b = max(b, pb[1]); }
+                            if (park) { pb[0] = a; pb[1] = b; }
+                        }
+                        if (!park) {
+                            emit_pair(p, qa, s, a);
+                            emit_pair(p, qb, s, b);
+                        }
                     }
                 } else {
                     // H[row][last column] is still in the lane's state: the last column pass built
@@ -305,12 +375,14 @@ gotoh_pair16_kernel(const ScoreParams p)
                                 : "+r"(v) : "r"(r + 1), "r"(k), "r"(Tn[k]));
                         return v;
                     };
-                    const int ra = La - 1 - i0, rb = Lb - 1 - i0;
+                    const int ra = La - 1 - gi0, rb = Lb - 1 - gi0;   // owned by this lane in this pass?
                     if (ra >= 0 && ra < K) emit_pair(p, qa, s, (int)(int16_t)(final_h(ra) & 0xFFFFu));
                     if (rb >= 0 && rb < K) emit_pair(p, qb, s, (int)(int16_t)(final_h(rb) >> 16));
                 }
+                // idle steps that keep the warp's streams in step (0 unless ALIGN_STREAMS)
+                const int pad = Cfg::ALIGN_STREAMS ? stream_len(ord) - 1 - p.seq_len[s] : 0;
                 ++ord;
-                if (ord < n_g) {
+                if (ord < n_g && pad == 0) {
                     const uint8_t *sn = p.codes + p.seq_off[s_first + ord * NGROUPS];
                     c1 = __ldg(sn);
                     c2 = __ldg(sn + 1);
@@ -320,21 +392,25 @@ gotoh_pair16_kernel(const ScoreParams p)
                     c1 = TOK_IDLE;
                     c2 = TOK_IDLE;
                     off = 0;
+                    wait = (ord < n_g) ? pad : 0;
                 }
             } else {
-                // ================= cold path: idle token (wind-up of lane t, or stream finished) ====
+                // ================= cold path: idle token (wind-up of lane t, between two subjects of
+                // an aligned stream, or stream finished) ====
                 off = 0;                        // stay on the header of idle bytes
                 if (wait > 0 && --wait == 0) {
-                    const uint8_t *s0 = p.codes + p.seq_off[s_first];
+                    const uint8_t *s0 = p.codes + p.seq_off[s_first + ord * NGROUPS];
                     c1 = __ldg(s0);
                     c2 = __ldg(s0 + 1);
-                    off = p.seq_off[s_first] + 1;
+                    off = p.seq_off[s_first + ord * NGROUPS] + 1;
                     begin_subject(c1);
                 }
             }
             c = c1;
             c1 = c2;
+            if (MP) { bnd = bnd1; bnd1 = bnd2; }
         }
+      }   // pass
     }
 }
 

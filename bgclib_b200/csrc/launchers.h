@@ -9,6 +9,10 @@ using Pair16Launcher = cudaError_t (*)(int K, const ScoreParams &p, int n_sm, cu
 #define BGCA_DECL_LAUNCH(G, M, P) \
     cudaError_t launch_pair16_g##G##_m##M##_p##P(int K, const ScoreParams &p, int n_sm, cudaStream_t st, int *grid_out);
 #define BGCA_DECL_LAUNCH_GM(G, M) BGCA_DECL_LAUNCH(G, M, 0) BGCA_DECL_LAUNCH(G, M, 1) BGCA_DECL_LAUNCH(G, M, 2)
+BGCA_DECL_LAUNCH_GM(1, 0)
+BGCA_DECL_LAUNCH_GM(1, 1)
+BGCA_DECL_LAUNCH_GM(2, 0)
+BGCA_DECL_LAUNCH_GM(2, 1)
 BGCA_DECL_LAUNCH_GM(4, 0)
 BGCA_DECL_LAUNCH_GM(4, 1)
 BGCA_DECL_LAUNCH_GM(8, 0)
@@ -17,6 +21,14 @@ BGCA_DECL_LAUNCH_GM(16, 0)
 BGCA_DECL_LAUNCH_GM(16, 1)
 BGCA_DECL_LAUNCH_GM(32, 0)
 BGCA_DECL_LAUNCH_GM(32, 1)
+// multi-pass (G = 32) instantiations
+#define BGCA_DECL_LAUNCH_MP(M, P) \
+    cudaError_t launch_pair16_mp_m##M##_p##P(int K, const ScoreParams &p, int n_sm, cudaStream_t st, int *grid_out);
+BGCA_DECL_LAUNCH_MP(0, 0) BGCA_DECL_LAUNCH_MP(0, 1) BGCA_DECL_LAUNCH_MP(0, 2)
+BGCA_DECL_LAUNCH_MP(1, 0) BGCA_DECL_LAUNCH_MP(1, 1) BGCA_DECL_LAUNCH_MP(1, 2)
+#undef BGCA_DECL_LAUNCH_MP
+// CTAs the multi-pass kernels are launched with at most (sizes their scratch lines)
+int pair16_mp_max_grid(int n_sm);
 #undef BGCA_DECL_LAUNCH_GM
 #undef BGCA_DECL_LAUNCH
 

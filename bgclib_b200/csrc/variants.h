@@ -8,11 +8,15 @@
     X(G, 13) X(G, 14) X(G, 15) X(G, 16) X(G, 17) X(G, 18) X(G, 19) X(G, 20) X(G, 21) X(G, 22)  \
     X(G, 23) X(G, 24) X(G, 25) X(G, 26) X(G, 27) X(G, 28) X(G, 29) X(G, 30) X(G, 31) X(G, 32)
 
-// Whole-warp variants with more than 32 rows per lane: queries of 1025..2048 residues (whole
-// proteins) in ONE pass, at one CTA per SM (the profile alone takes up to 213 KB of shared memory).
-#define BGCA_K_LIST_WIDE(X, G) X(G, 40) X(G, 48) X(G, 56) X(G, 64)
+// Multi-pass whole-warp variants: a query of more than 1024 residues is swept in
+// ceil(L / (32*K)) passes of 32*K rows (K = 17..32 covers every length), see gotoh_pair16.cuh.
+#define BGCA_K_LIST_MP(X, G) \
+    X(G, 17) X(G, 18) X(G, 19) X(G, 20) X(G, 21) X(G, 22) X(G, 23) X(G, 24) X(G, 25) X(G, 26) \
+    X(G, 27) X(G, 28) X(G, 29) X(G, 30) X(G, 31) X(G, 32)
 
 #define BGCA_VARIANTS(X) \
-    BGCA_K_LIST(X, 4) BGCA_K_LIST(X, 8) BGCA_K_LIST(X, 16) BGCA_K_LIST(X, 32) BGCA_K_LIST_WIDE(X, 32)
+    BGCA_K_LIST(X, 1) BGCA_K_LIST(X, 2) BGCA_K_LIST(X, 4) BGCA_K_LIST(X, 8) BGCA_K_LIST(X, 16) BGCA_K_LIST(X, 32)
 
+#define BGCA_VARIANT_MP 0x10000   /* flag in bgca_tile.variant: multi-pass instantiation */
 #define BGCA_VARIANT_ID(G, K) (((G) << 8) | (K))
+#define BGCA_ONE_PASS_ROWS 1024   /* longest query of a single-pass variant (G = 32, K = 32) */

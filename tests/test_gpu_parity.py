@@ -59,7 +59,7 @@ def test_random_lengths_bit_exact(mode, lo, hi):
     assert res.plan["n_fallback32"] == 0
 
 
-@pytest.mark.parametrize("force_g", ["4", "8", "16", "32"])
+@pytest.mark.parametrize("force_g", ["1", "2", "4", "8", "16", "32"])
 def test_every_group_width(monkeypatch, force_g):
     monkeypatch.setenv("BGCA_FORCE_G", force_g)
     rng = np.random.default_rng(int(force_g))
@@ -96,14 +96,39 @@ def test_long_sequences_take_the_32bit_kernel():
 
 @pytest.mark.parametrize("mode", ["local", "global"])
 def test_protein_length_queries_stay_on_the_packed_kernel(mode):
-    """Queries of 1025..2048 residues run in ONE pass of the whole-warp variants with 40..64
-    rows per lane (no 32-bit fallback)."""
+    """Queries of more than 1024 residues run as a multi-pass sweep of the whole-warp packed
+    kernel (bottom row of a pass parked for the next one) — no 32-bit fallback while the scores
+    fit int16.  Pass boundaries 1024/1025, 2048/2049 and the two halves of a query pair ending in
+    different passes are all in here."""
     rng = np.random.default_rng(17 + (mode == "global"))
-    seqs = _related(rng, 2, 4, 1025, 2048) + [_rand(rng, k) for k in (1025, 1280, 1281, 1536, 1793, 2047, 2048, 90)]
+    seqs = _related(rng, 2, 4, 1025, 2048) + [_rand(rng, k) for k in (1024, 1025, 1280, 1281, 1536, 1793, 2047, 2048,
+                                                                     2049, 2500, 90)]
     res = domain_pair_scores(seqs, mode=mode)
     assert res.plan["n_fallback32"] == 0
     cm = oracle.MODE_LOCAL if mode == "local" else oracle.MODE_GLOBAL
     assert (res.scores == oracle.all_pairs(seqs, mode=cm)).all()
+
+
+@pytest.mark.parametrize("mode", ["local", "global"])
+def test_multi_pass_many_subjects_and_long_queries(mode):
+    """The multi-pass sweep with full tiles (several subjects per group, so the parked line is
+    indexed across subject boundaries), three- and six-pass queries against short database
+    domains (cross plan), other gap scores (run-time gap kernels), and the fused rowbest epilogue."""
+    rng = np.random.default_rng(23 + (mode == "global"))
+    base = _rand(rng, 6000)
+    long_q = [base[:1100], base[300:1700], base[:2100], base[100:3000], base[:6000], _rand(rng, 1300)]
+    short = _related(rng, 3, 8, 60, 500) + [base[k:k + 300] for k in range(0, 5400, 450)]
+    cm = oracle.MODE_LOCAL if mode == "local" else oracle.MODE_GLOBAL
+    res = domain_pair_scores(long_q, database=short, mode=mode)
+    assert res.plan["n_fallback32"] == 0
+    full = oracle.all_pairs(long_q + short, mode=cm)
+    assert (res.scores == full[: len(long_q), len(long_q):]).all()
+    # square plan: 40 sequences of 1025..1500 residues -> tiles with several subjects per group
+    many = _related(rng, 4, 10, 1025, 1500)
+    for o, e in ((-12, -1), (-7, -2)):
+        res = domain_pair_scores(many, mode=mode, open_gap_score=o, extend_gap_score=e)
+        assert res.plan["n_fallback32"] == 0
+        assert (res.scores == oracle.all_pairs(many, mode=cm, open_gap=o, extend_gap=e)).all(), (o, e)
 
 
 def test_literature_known_answers():
@@ -122,9 +147,9 @@ def test_literature_known_answers():
 
 
 def test_long_queries_against_a_persistent_database():
-    """Queries beyond the packed kernel's reach (> 2048 residues) and a global-mode int16 overflow
-    against a PackedDatabase: the 32-bit fallback list must hold every query x database pair
-    although the database sorts in FRONT of its queries."""
+    """Queries longer than one pass against a PackedDatabase — on the multi-pass packed kernel,
+    and, with gap scores that leave int16 in global mode, on the 32-bit kernel, whose pair list
+    must hold every query x database pair although the database sorts in FRONT of its queries."""
     from bgclib_b200 import PackedDatabase
     rng = np.random.default_rng(41)
     base = _rand(rng, 2700)
@@ -132,10 +157,16 @@ def test_long_queries_against_a_persistent_database():
     q_seqs = [base[:2500], base[60:2660], base[100:400]]
     db = PackedDatabase(db_seqs)
     for mode, cm in (("local", oracle.MODE_LOCAL), ("global", oracle.MODE_GLOBAL)):
-        dps = domain_pair_scores(q_seqs, database=db, mode=mode)
-        assert dps.plan["n_fallback32"] >= 1
-        full = oracle.all_pairs(q_seqs + db_seqs, mode=cm)
-        assert (dps.scores == full[:3, 3:]).all(), mode
+        for (o, e), fallback in (((-12, -1), False), ((-40, -40), mode == "global")):
+            dps = domain_pair_scores(q_seqs, database=db, mode=mode, open_gap_score=o, extend_gap_score=e)
+            assert (dps.plan["n_fallback32"] >= 1) == fallback, (mode, o, e)
+            full = oracle.all_pairs(q_seqs + db_seqs, mode=cm, open_gap=o, extend_gap=e)
+            assert (dps.scores == full[:3, 3:]).all(), (mode, o, e)
+    # local scores that leave int16 (W-rich, > 2727 residues on both sides): 32-bit kernel again
+    wq, wdb = ["W" * 2800 + base[:50], base[:90]], ["WY" * 1400, "W" * 2750, base[20:200]]
+    dps = domain_pair_scores(wq, database=PackedDatabase(wdb))
+    assert dps.plan["n_fallback32"] >= 1
+    assert (dps.scores == oracle.all_pairs(wq + wdb)[:2, 2:]).all()
     # the fused similarity on the same plan shape (rowbest of the long queries must not stay 0)
     from bgclib_b200.extract import DomainBatch, DomainRecord
 

@@ -92,7 +92,7 @@ def test_planner_balance_and_variants():
         tiles, info = plan_host(lens, rank=r, world=8)
         loads.append(info["cells_computed"])
         for v in set(tiles["variant"].tolist()):
-            G, K = v >> 8, v & 0xFF
+            G, K = (v >> 8) & 0xFF, v & 0xFF
             sel = tiles[tiles["variant"] == v]
             lq = np.maximum(lens[sel["qa"]], np.where(sel["qb"] >= 0, lens[np.maximum(sel["qb"], 0)], 0))
             assert G in (8, 16, 32) and (G * K >= lq).all()
@@ -112,11 +112,17 @@ def test_planner_balance_and_variants():
     for t in tiles:
         if t["s_begin"] <= 2 < t["s_end"]:
             assert t["variant"] == 0, "a 30000-residue subject in global mode must take the 32-bit kernel"
-    # a persistent database in front of two queries beyond the packed kernel's reach: the cross
-    # tiles fall back to the 32-bit kernel and still account for every query x database pair
+    # a persistent database in front of two queries longer than one pass of the packed kernel: the
+    # cross tiles take the multi-pass variants and account for every query x database pair
     lens_db = np.array([100, 120, 150, 200, 220, 300, 2500, 2600], np.int32)
     tiles, info = plan_host(lens_db, cross_only=2, n_db_first=6)
-    assert info["n_fallback32"] >= 1 and info["total_pairs"] == 2 * 6 + 2
+    assert info["n_fallback32"] == 0 and info["total_pairs"] == 2 * 6 + 2
+    assert all(int(t["variant"]) & 0x10000 for t in tiles)              # BGCA_VARIANT_MP
+    assert {int(t["variant"]) & 0xFFFF for t in tiles} == {(32 << 8) | 28}   # ceil(2600 / (32 * 3)) rows per lane
+    # ... and the 32-bit kernel when the scores can leave int16 (11 * min length > 30000)
+    lens_big = np.array([2800, 2900, 3000, 3100, 3200, 3300, 3400, 3500], np.int32)
+    tiles, info = plan_host(lens_big, cross_only=2, n_db_first=6)
+    assert info["n_fallback32"] == info["n_tiles"] and info["total_pairs"] == 2 * 6 + 2
 
 
 def test_extract_from_collection():
