@@ -29,6 +29,7 @@ CFLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--cud
 UNITS = [("bgca_api.o", "bgca_api.cu", []),
          ("pack_reduce.o", "pack_reduce.cu", []),
          ("stats.o", "stats.cu", []),
+         ("stats2.o", "stats2.cu", []),
          ("dpx_probe.o", "dpx_probe.cu", [])]
 for g in (1, 2, 4, 8, 16, 32):
     for m in (0, 1):

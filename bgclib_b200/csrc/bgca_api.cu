@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 
+#include "gotoh_stats2.cuh"
 #include "launchers.h"
 #include "variants.h"
 
@@ -429,6 +430,7 @@ struct bgca_engine {
     DevBuf<int2> d_scratch, d_mp_scratch;
     DevBuf<uint4> d_scratch_st;
     DevBuf<int32_t> d_scores_host_call;   // bgca_score_all_host's n x n staging matrix
+    DevBuf<int32_t> d_st2_items;          // K7 work items (Stats2Item = 4 x int32)
     // plan
     std::vector<bgca_tile> tiles;
     bgca_plan_info plan_info{};
@@ -493,7 +495,7 @@ int bgca_destroy(bgca_engine *e)
     e->d_ascii.release(); e->d_codes.release(); e->d_offsets_orig.release(); e->d_order.release();
     e->d_len.release(); e->d_type.release(); e->d_bgc.release(); e->d_bgc_start.release();
     e->d_bgc_doms.release(); e->d_counters.release(); e->d_pq.release(); e->d_ps.release();
-    e->d_seq_off.release(); e->d_err.release(); e->d_tiles.release(); e->d_scratch.release(); e->d_mp_scratch.release(); e->d_scratch_st.release(); e->d_scores_host_call.release();
+    e->d_seq_off.release(); e->d_err.release(); e->d_tiles.release(); e->d_scratch.release(); e->d_mp_scratch.release(); e->d_scratch_st.release(); e->d_scores_host_call.release(); e->d_st2_items.release();
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->evp0) cudaEventDestroy(e->evp0);
@@ -1074,7 +1076,8 @@ try {
 // ORIGINAL-space device pair lists -> SORTED-space lists in e->d_pq / e->d_ps (lists are small
 // on these explicit-pair paths, so the translation runs on the host)
 static int stage_pair_list(bgca_engine *e, const int32_t *pi, const int32_t *pj, int64_t npairs,
-                           int max_len_allowed, const char *who, cudaStream_t st, int *max_len_seen = nullptr)
+                           int max_len_allowed, const char *who, cudaStream_t st, int *max_len_seen = nullptr,
+                           std::vector<int32_t> *sorted_q = nullptr, std::vector<int32_t> *sorted_s = nullptr)
 {
     int longest = 0;
     std::vector<int32_t> hi(npairs), hj(npairs);
@@ -1097,6 +1100,76 @@ static int stage_pair_list(bgca_engine *e, const int32_t *pi, const int32_t *pj,
     CUDA_TRY(cudaMemcpyAsync(e->d_ps.p, hj.data(), sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (max_len_seen) *max_len_seen = longest;
+    if (sorted_q) sorted_q->swap(hi);
+    if (sorted_s) sorted_s->swap(hj);
+    return BGCA_OK;
+}
+
+// K7, second form: pairs (SORTED indices hq, hs) grouped by query into work items of at most
+// kStats2ItemPairs pairs, one item list and launch per rows-per-lane class of the query.
+constexpr int kStats2ItemPairs = 32;
+static int run_stats2(bgca_engine *e, const std::vector<int32_t> &hq, const std::vector<int32_t> &hs,
+                      bgca_alnstats *out, cudaStream_t st)
+{
+    const int64_t npairs = (int64_t)hq.size();
+    std::vector<int32_t> idx(npairs);
+    std::iota(idx.begin(), idx.end(), 0);
+    std::stable_sort(idx.begin(), idx.end(), [&](int32_t a, int32_t b) { return hq[a] < hq[b]; });
+    std::vector<int32_t> subj(npairs);
+    for (int64_t k = 0; k < npairs; ++k) subj[k] = hs[idx[k]];
+    static const int ks_list[] = {BGCA_STATS2_KS_LIST};
+    constexpr int n_cls = sizeof(ks_list) / sizeof(ks_list[0]);
+    std::vector<Stats2Item> items[n_cls];
+    for (int64_t a = 0; a < npairs;) {
+        int64_t b = a;
+        const int q = hq[idx[a]];
+        while (b < npairs && hq[idx[b]] == q) ++b;
+        const int ks = stats2_rows_per_lane(e->len[q]);
+        int cls = 0;
+        while (ks_list[cls] != ks) ++cls;
+        for (int64_t f = a; f < b; f += kStats2ItemPairs)
+            items[cls].push_back(Stats2Item{q, (int32_t)f, (int32_t)std::min<int64_t>(kStats2ItemPairs, b - f), 0});
+        a = b;
+    }
+    size_t n_items = 0;
+    for (auto &v : items) n_items += v.size();
+    std::vector<Stats2Item> flat;
+    flat.reserve(n_items);
+    for (auto &v : items) flat.insert(flat.end(), v.begin(), v.end());
+    CUDA_TRY(e->d_pq.reserve(npairs));                      // subjects, grouped
+    CUDA_TRY(e->d_ps.reserve(npairs));                      // caller's position of each grouped pair
+    CUDA_TRY(e->d_st2_items.reserve(flat.size() * 4));
+    CUDA_TRY(e->d_counters.reserve(n_cls + 1));
+    CUDA_TRY(cudaMemcpyAsync(e->d_pq.p, subj.data(), sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->d_ps.p, idx.data(), sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->d_st2_items.p, flat.data(), sizeof(Stats2Item) * flat.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(e->d_counters.p, 0, sizeof(int32_t) * (n_cls + 1), st));
+    CUDA_TRY(cudaStreamSynchronize(st));                    // the host vectors above die with this frame
+    Stats2Params sp;
+    std::memset(&sp, 0, sizeof(sp));
+    sp.codes = e->d_codes.p;
+    sp.seq_off = e->d_seq_off.p;
+    sp.seq_len = e->d_len.p;
+    sp.subj = e->d_pq.p;
+    sp.out_idx = e->d_ps.p;
+    sp.out = out;
+    sp.open = e->open;
+    sp.extend = e->extend;
+    std::memcpy(sp.sub, e->sub, NSYM * NSYM);
+    e->last_launches = 0;
+    size_t first = 0;
+    CUDA_TRY(cudaEventRecord(e->ev0, st));
+    for (int c = 0; c < n_cls; ++c) {
+        if (items[c].empty()) continue;
+        sp.items = reinterpret_cast<const Stats2Item *>(e->d_st2_items.p) + first;
+        sp.n_items = (int32_t)items[c].size();
+        sp.item_counter = e->d_counters.p + c;
+        CUDA_TRY(launch_stats2(e->mode, ks_list[c], sp, e->n_sm, st));
+        e->last_launches++;
+        first += items[c].size();
+    }
+    CUDA_TRY(cudaEventRecord(e->ev1, st));
+    e->timed = true;
     return BGCA_OK;
 }
 
@@ -1127,10 +1200,17 @@ try {
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(e->device));
     int longest = 0;
-    int rc = stage_pair_list(e, pi, pj, npairs, 32767, "bgca_pair_stats", st, &longest);
+    std::vector<int32_t> hq, hs;
+    int rc = stage_pair_list(e, pi, pj, npairs, 32767, "bgca_pair_stats", st, &longest, &hq, &hs);
     if (rc != BGCA_OK) return rc;
     // every protein domain fits the one-word tuple; longer sequences take the 96-bit one
     const int compact = (longest <= 1023 && e->max_abs_sub * 1023 < (1 << 21) && -e->open < 1000 && -e->extend < 1000);
+    // ... and the FP64-compare form of it (gotoh_stats2.cuh) when every DP value stays well inside
+    // the +-2^19 its biased score field holds (it does for any protein matrix and gap scores in use)
+    const long long worst = 3LL * -e->open + (long long)-e->extend * (2 * longest + 2) +
+                            (long long)e->max_abs_sub * longest + 4096;
+    if (compact && longest <= ST2_MAXLEN && worst < (1 << 19) - 4096 && !std::getenv("BGCA_STATS_V1"))
+        return run_stats2(e, hq, hs, out, st);
     ScoreParams p;
     fill_params(e, p, nullptr, nullptr, nullptr, 0);
     int max_len = 0;
@@ -1141,7 +1221,10 @@ try {
         grid = (int)std::max<long long>(1, (npairs + warps_per_cta - 1) / warps_per_cta);
     const int stride = (max_len + 3) & ~3;
     CUDA_TRY(e->d_scratch_st.reserve((size_t)grid * warps_per_cta * 2 * stride));
+    CUDA_TRY(cudaEventRecord(e->ev0, st));
     CUDA_TRY(launch_stats(e->mode, compact, p, e->d_pq.p, e->d_ps.p, npairs, e->d_scratch_st.p, stride, out, grid, st));
+    CUDA_TRY(cudaEventRecord(e->ev1, st));
+    e->timed = true;
     e->last_launches = 1;
     return BGCA_OK;
 } catch (const std::exception &ex) {   // std::bad_alloc and friends must not cross the C ABI

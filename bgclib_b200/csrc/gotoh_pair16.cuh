@@ -82,7 +82,14 @@ template <int G, int K>
 struct Pair16Cfg {
     static constexpr int CH = (K + 3) / 4;          // 16-byte chunks per lane per letter
     static constexpr int LPAD = G * K;              // query rows covered in one pass
-    static constexpr int ROW_BYTES = CH * G * 16;   // one profile row (multiple of 128 B)
+    // A quarter-warp (8 lanes) is served by one LDS.128 wavefront when its lanes hit 8 distinct
+    // 16-byte bank groups.  With G >= 8 the 8 lanes are 8 different t of one group: 8 distinct
+    // columns of the same row.  With G < 8 they belong to 8/G groups that look up DIFFERENT
+    // letters (rows) at the same t, so the profile is replicated 8/G times and every lane of a
+    // quarter-warp owns its own column (lane & 7) whatever row it reads.
+    static constexpr int REP = (G < 8) ? 8 / G : 1;
+    static constexpr int W = G * REP;               // 16-byte columns per chunk row
+    static constexpr int ROW_BYTES = CH * W * 16;   // one profile row (multiple of 128 B)
     static constexpr int NGROUPS = CTA_THREADS / G; // alignment groups (subject streams) per CTA
     static constexpr int PROF_BYTES = PROF_ROWS * ROW_BYTES;
     // per group a ring of (lo, hi) best slots: lane 0 can run at most G-1 subjects ahead of the
@@ -126,7 +133,7 @@ gotoh_pair16_kernel(const ScoreParams p)
     constexpr unsigned FULL = 0xFFFFFFFFu;
 
     extern __shared__ uint4 smem_u4[];
-    uint4 *prof = smem_u4;                                                    // [PROF_ROWS][CH][G]
+    uint4 *prof = smem_u4;                                                    // [PROF_ROWS][CH][W]
     int *sbest = reinterpret_cast<int *>(reinterpret_cast<uint8_t *>(smem_u4) + Cfg::PROF_BYTES);
     uint8_t *qcodes = reinterpret_cast<uint8_t *>(sbest) + Cfg::BEST_BYTES;   // [2][LPAD]
     int8_t *ssub = reinterpret_cast<int8_t *>(qcodes + 2 * LPAD);
@@ -149,7 +156,7 @@ gotoh_pair16_kernel(const ScoreParams p)
     const uint8_t *const idle_ptr = p.codes;            // header of the packed batch: TOK_IDLE bytes
     int *const my_best = sbest + gid * (Cfg::RING * 2);
     // this lane's 16-byte column of the profile, as a 32-bit shared-window address
-    const uint32_t prof_lane = (uint32_t)__cvta_generic_to_shared(prof) + (uint32_t)t * 16u;
+    const uint32_t prof_lane = (uint32_t)__cvta_generic_to_shared(prof) + (uint32_t)(G < 8 ? (lane & 7) : t) * 16u;
 
     for (;;) {
         if (tid == 0) s_tile = atomicAdd(p.tile_counter, 1);
@@ -191,8 +198,10 @@ gotoh_pair16_kernel(const ScoreParams p)
                 const int sa = ((ca < NSYM && b < NSYM) ? ssub[ca * NSYM + b] : 0) - p.open;
                 const int sb = ((cb < NSYM && b < NSYM) ? ssub[cb * NSYM + b] : 0) - p.open;
                 const int tt = pos / K, k = pos - tt * K;
-                pw[(((b * CH) + (k >> 2)) * G + tt) * 4 + (k & 3)] =
-                    ((uint32_t)sa & 0xFFFFu) | ((uint32_t)sb << 16);
+                const uint32_t word = ((uint32_t)sa & 0xFFFFu) | ((uint32_t)sb << 16);
+#pragma unroll
+                for (int r = 0; r < Cfg::REP; ++r)
+                    pw[(((b * CH) + (k >> 2)) * Cfg::W + r * G + tt) * 4 + (k & 3)] = word;
             }
         }
         __syncthreads();
@@ -239,7 +248,7 @@ gotoh_pair16_kernel(const ScoreParams p)
             uint32_t P[CH * 4];
 #pragma unroll
             for (int ch = 0; ch < CH; ++ch) {
-                const uint4 v = lds128(a + ch * (G * 16));
+                const uint4 v = lds128(a + ch * (Cfg::W * 16));
                 P[ch * 4 + 0] = v.x; P[ch * 4 + 1] = v.y; P[ch * 4 + 2] = v.z; P[ch * 4 + 3] = v.w;
             }
             // Ho[i0+k][-1], walked down the rows.  The empty asm makes the start value opaque so
@@ -309,7 +318,7 @@ gotoh_pair16_kernel(const ScoreParams p)
                     uint32_t P[CH * 4];
 #pragma unroll
                     for (int ch = 0; ch < CH; ++ch) {
-                        const uint4 v = lds128(a + ch * (G * 16));
+                        const uint4 v = lds128(a + ch * (Cfg::W * 16));
                         P[ch * 4 + 0] = v.x; P[ch * 4 + 1] = v.y; P[ch * 4 + 2] = v.z; P[ch * 4 + 3] = v.w;
                     }
                     uint32_t up = h_in, F = f_in, h_prev = 0;

@@ -41,6 +41,12 @@ cudaError_t launch_stats(int mode, int compact, const ScoreParams &p, const int3
                          long long npairs, uint4 *scratch, int scratch_stride, bgca_alnstats *out,
                          int grid, cudaStream_t st);
 
+// K7 second form (stats2.cu): sequences of at most 1023 residues, pairs grouped by query
+#define BGCA_STATS2_KS_LIST 4, 8, 12, 16, 24, 32
+struct Stats2Params;
+int stats2_rows_per_lane(int La);
+cudaError_t launch_stats2(int mode, int KS, const Stats2Params &p, int n_sm, cudaStream_t st);
+
 // K1 / K5 kernels (pack_reduce.cu)
 cudaError_t launch_pack(const uint8_t *ascii, const int64_t *src_off_sorted, const int32_t *order,
                         const uint32_t *seq_off, const int32_t *seq_len, int32_t n, uint8_t *codes,

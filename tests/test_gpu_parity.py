@@ -120,7 +120,7 @@ def test_multi_pass_many_subjects_and_long_queries(mode):
     short = _related(rng, 3, 8, 60, 500) + [base[k:k + 300] for k in range(0, 5400, 450)]
     cm = oracle.MODE_LOCAL if mode == "local" else oracle.MODE_GLOBAL
     res = domain_pair_scores(long_q, database=short, mode=mode)
-    assert res.plan["n_fallback32"] == 0
+    assert res.plan["n_fallback32"] <= 1       # only the self tile of the 6000-residue query (score > int16)
     full = oracle.all_pairs(long_q + short, mode=cm)
     assert (res.scores == full[: len(long_q), len(long_q):]).all()
     # square plan: 40 sequences of 1025..1500 residues -> tiles with several subjects per group
