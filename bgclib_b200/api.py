@@ -456,15 +456,26 @@ def domain_pair_stats(source, pairs=None, *, mode="local", matrix="BLOSUM62", op
     n = len(batch)
     if n == 0:
         raise ValueError("no domain sequences selected")
+    known = None
+    dist, rank, world = _dist()
     if pairs is None and min_score is not None:
         sc = domain_pair_scores(batch, mode=mode, matrix=matrix, open_gap_score=open_gap_score,
                                 extend_gap_score=extend_gap_score, same_type_only=same_type_only,
                                 device=device, return_device=True)
         t = sc.scores
+        if dist is None:
+            # one process: the engine still holds the batch the scoring pass packed; pairs are
+            # selected on the device and carry their scores as hints (bgca_select_pairs)
+            eng = get_engine(device)
+            pairs_t, out = eng.pair_stats_above(t.contiguous(), int(min_score), same_type_only)
+            stats = np.ascontiguousarray(out.cpu().numpy()).view(ALNSTAT_DTYPE).reshape(-1)
+            return DomainPairStats(stats, pairs_t.cpu().numpy(), batch.records)
         keep = t >= int(min_score)
         if sc.computed is not None:
             keep &= sc.computed
-        pairs = keep.triu(diagonal=1).nonzero().to("cpu").numpy()     # row-major: sorted by (i, j)
+        sel = keep.triu(diagonal=1).nonzero()                         # row-major: sorted by (i, j)
+        known = t[sel[:, 0], sel[:, 1]].to("cpu").numpy()
+        pairs = sel.to("cpu").numpy()
     elif pairs is None:
         iu = np.triu_indices(n, k=1)
         pairs = np.stack(iu, axis=1)
@@ -474,7 +485,6 @@ def domain_pair_stats(source, pairs=None, *, mode="local", matrix="BLOSUM62", op
     eng = get_engine(device)
     eng.set_scoring(matrix, open_gap_score, extend_gap_score, mode)
     eng.pack(batch.sequences)
-    dist, rank, world = _dist()
     if dist is None:
         out = eng.pair_stats(pairs[:, 0].copy(), pairs[:, 1].copy())
     else:
@@ -483,7 +493,8 @@ def domain_pair_stats(source, pairs=None, *, mode="local", matrix="BLOSUM62", op
         out = eng.torch.zeros((len(pairs), len(ALNSTAT_DTYPE.names)), dtype=eng.torch.int32, device=eng.tdev)
         mine = np.arange(rank, len(pairs), world)
         if len(mine):
-            out[eng.torch.as_tensor(mine, device=eng.tdev)] = eng.pair_stats(pairs[mine, 0].copy(), pairs[mine, 1].copy())
+            out[eng.torch.as_tensor(mine, device=eng.tdev)] = eng.pair_stats(
+                pairs[mine, 0].copy(), pairs[mine, 1].copy(), None if known is None else known[mine].copy())
         dist.all_reduce(out, op=dist.ReduceOp.SUM)
     stats = np.ascontiguousarray(out.cpu().numpy()).view(ALNSTAT_DTYPE).reshape(-1)
     return DomainPairStats(stats, pairs, batch.records)

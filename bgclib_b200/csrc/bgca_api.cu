@@ -431,6 +431,14 @@ struct bgca_engine {
     DevBuf<uint4> d_scratch_st;
     DevBuf<int32_t> d_scores_host_call;   // bgca_score_all_host's n x n staging matrix
     DevBuf<int32_t> d_st2_items;          // K7 work items (Stats2Item = 4 x int32)
+    DevBuf<int32_t> d_st2_hint;           // K7: known best scores of the grouped pairs
+    // pair selection by score (bgca_select_pairs -> bgca_pair_stats_selected)
+    DevBuf<int32_t> d_inv_order, d_sel_cnt, d_sel_cls;
+    DevBuf<int64_t> d_sel_rowstart;
+    bool sel_valid = false;
+    int32_t sel_min_score = 0, sel_same_type = 0;
+    int64_t sel_total = 0;
+    int32_t sel_cls_items[16] = {0};
     // plan
     std::vector<bgca_tile> tiles;
     bgca_plan_info plan_info{};
@@ -495,7 +503,8 @@ int bgca_destroy(bgca_engine *e)
     e->d_ascii.release(); e->d_codes.release(); e->d_offsets_orig.release(); e->d_order.release();
     e->d_len.release(); e->d_type.release(); e->d_bgc.release(); e->d_bgc_start.release();
     e->d_bgc_doms.release(); e->d_counters.release(); e->d_pq.release(); e->d_ps.release();
-    e->d_seq_off.release(); e->d_err.release(); e->d_tiles.release(); e->d_scratch.release(); e->d_mp_scratch.release(); e->d_scratch_st.release(); e->d_scores_host_call.release(); e->d_st2_items.release();
+    e->d_seq_off.release(); e->d_err.release(); e->d_tiles.release(); e->d_scratch.release(); e->d_mp_scratch.release(); e->d_scratch_st.release(); e->d_scores_host_call.release(); e->d_st2_items.release(); e->d_st2_hint.release();
+    e->d_inv_order.release(); e->d_sel_cnt.release(); e->d_sel_cls.release(); e->d_sel_rowstart.release();
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->evp0) cudaEventDestroy(e->evp0);
@@ -1105,72 +1114,114 @@ static int stage_pair_list(bgca_engine *e, const int32_t *pi, const int32_t *pj,
     return BGCA_OK;
 }
 
-// K7, second form: pairs (SORTED indices hq, hs) grouped by query into work items of at most
-// kStats2ItemPairs pairs, one item list and launch per rows-per-lane class of the query.
+// K7, second form.  Work items of at most kStats2ItemPairs pairs of one query, one item list and
+// launch per rows-per-lane class of the query.
 constexpr int kStats2ItemPairs = 32;
+static const int kStats2Ks[] = {BGCA_STATS2_KS_LIST};
+constexpr int kStats2Classes = sizeof(kStats2Ks) / sizeof(kStats2Ks[0]);
+
+// Launches over device-resident grouped pairs: items [cls_first[c], cls_first[c+1]) belong to
+// class c.  hint != NULL (local mode): the kernels that take the best score as known; should a
+// hint prove too high the whole list runs again without hints (exact either way).
+static int launch_stats2_classes(bgca_engine *e, const Stats2Item *d_items, const size_t *cls_first,
+                                 const int32_t *d_subj, const int32_t *d_out_idx, const int32_t *d_hint,
+                                 bgca_alnstats *out, cudaStream_t st)
+{
+    Stats2Params sp;
+    std::memset(&sp, 0, sizeof(sp));
+    sp.codes = e->d_codes.p;
+    sp.seq_off = e->d_seq_off.p;
+    sp.seq_len = e->d_len.p;
+    sp.subj = d_subj;
+    sp.out_idx = d_out_idx;
+    sp.out = out;
+    sp.open = e->open;
+    sp.extend = e->extend;
+    sp.openh = e->open * 1024;
+    sp.exth = e->extend * 1024;
+    std::memcpy(sp.sub, e->sub, NSYM * NSYM);
+    const bool hinted = d_hint != nullptr && e->mode == BGCA_MODE_LOCAL;
+    CUDA_TRY(e->d_counters.reserve(2 * kStats2Classes + 2));
+    e->last_launches = 0;
+    CUDA_TRY(cudaEventRecord(e->ev0, st));
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const bool use_hint = hinted && attempt == 0;
+        CUDA_TRY(cudaMemsetAsync(e->d_counters.p, 0, sizeof(int32_t) * (kStats2Classes + 2), st));
+        sp.hint = use_hint ? d_hint : nullptr;
+        sp.redo_count = e->d_counters.p + kStats2Classes;
+        for (int c = 0; c < kStats2Classes; ++c) {
+            if (cls_first[c + 1] == cls_first[c]) continue;
+            sp.items = d_items + cls_first[c];
+            sp.n_items = (int32_t)(cls_first[c + 1] - cls_first[c]);
+            sp.item_counter = e->d_counters.p + c;
+            CUDA_TRY(launch_stats2(e->mode, kStats2Ks[c], sp, e->n_sm, st));
+            e->last_launches++;
+        }
+        if (!use_hint) break;
+        CUDA_TRY(cudaEventRecord(e->ev1, st));
+        int32_t redo = 0;
+        CUDA_TRY(cudaMemcpyAsync(&redo, sp.redo_count, sizeof(redo), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (redo == 0) { e->timed = true; return BGCA_OK; }
+    }
+    CUDA_TRY(cudaEventRecord(e->ev1, st));
+    e->timed = true;
+    return BGCA_OK;
+}
+
+// explicit pair list (SORTED indices hq, hs; optional known scores): grouped by query on the host
 static int run_stats2(bgca_engine *e, const std::vector<int32_t> &hq, const std::vector<int32_t> &hs,
-                      bgca_alnstats *out, cudaStream_t st)
+                      const std::vector<int32_t> *known, bgca_alnstats *out, cudaStream_t st)
 {
     const int64_t npairs = (int64_t)hq.size();
     std::vector<int32_t> idx(npairs);
     std::iota(idx.begin(), idx.end(), 0);
     std::stable_sort(idx.begin(), idx.end(), [&](int32_t a, int32_t b) { return hq[a] < hq[b]; });
-    std::vector<int32_t> subj(npairs);
+    std::vector<int32_t> subj(npairs), hint(known ? npairs : 0);
     for (int64_t k = 0; k < npairs; ++k) subj[k] = hs[idx[k]];
-    static const int ks_list[] = {BGCA_STATS2_KS_LIST};
-    constexpr int n_cls = sizeof(ks_list) / sizeof(ks_list[0]);
-    std::vector<Stats2Item> items[n_cls];
+    if (known)
+        for (int64_t k = 0; k < npairs; ++k) hint[k] = (*known)[idx[k]];
+    std::vector<Stats2Item> items[kStats2Classes];
     for (int64_t a = 0; a < npairs;) {
         int64_t b = a;
         const int q = hq[idx[a]];
         while (b < npairs && hq[idx[b]] == q) ++b;
         const int ks = stats2_rows_per_lane(e->len[q]);
         int cls = 0;
-        while (ks_list[cls] != ks) ++cls;
+        while (kStats2Ks[cls] != ks) ++cls;
         for (int64_t f = a; f < b; f += kStats2ItemPairs)
             items[cls].push_back(Stats2Item{q, (int32_t)f, (int32_t)std::min<int64_t>(kStats2ItemPairs, b - f), 0});
         a = b;
     }
-    size_t n_items = 0;
-    for (auto &v : items) n_items += v.size();
     std::vector<Stats2Item> flat;
-    flat.reserve(n_items);
-    for (auto &v : items) flat.insert(flat.end(), v.begin(), v.end());
+    size_t cls_first[kStats2Classes + 1] = {0};
+    for (int c = 0; c < kStats2Classes; ++c) {
+        flat.insert(flat.end(), items[c].begin(), items[c].end());
+        cls_first[c + 1] = flat.size();
+    }
     CUDA_TRY(e->d_pq.reserve(npairs));                      // subjects, grouped
     CUDA_TRY(e->d_ps.reserve(npairs));                      // caller's position of each grouped pair
     CUDA_TRY(e->d_st2_items.reserve(flat.size() * 4));
-    CUDA_TRY(e->d_counters.reserve(n_cls + 1));
     CUDA_TRY(cudaMemcpyAsync(e->d_pq.p, subj.data(), sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(e->d_ps.p, idx.data(), sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(e->d_st2_items.p, flat.data(), sizeof(Stats2Item) * flat.size(), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemsetAsync(e->d_counters.p, 0, sizeof(int32_t) * (n_cls + 1), st));
-    CUDA_TRY(cudaStreamSynchronize(st));                    // the host vectors above die with this frame
-    Stats2Params sp;
-    std::memset(&sp, 0, sizeof(sp));
-    sp.codes = e->d_codes.p;
-    sp.seq_off = e->d_seq_off.p;
-    sp.seq_len = e->d_len.p;
-    sp.subj = e->d_pq.p;
-    sp.out_idx = e->d_ps.p;
-    sp.out = out;
-    sp.open = e->open;
-    sp.extend = e->extend;
-    std::memcpy(sp.sub, e->sub, NSYM * NSYM);
-    e->last_launches = 0;
-    size_t first = 0;
-    CUDA_TRY(cudaEventRecord(e->ev0, st));
-    for (int c = 0; c < n_cls; ++c) {
-        if (items[c].empty()) continue;
-        sp.items = reinterpret_cast<const Stats2Item *>(e->d_st2_items.p) + first;
-        sp.n_items = (int32_t)items[c].size();
-        sp.item_counter = e->d_counters.p + c;
-        CUDA_TRY(launch_stats2(e->mode, ks_list[c], sp, e->n_sm, st));
-        e->last_launches++;
-        first += items[c].size();
+    if (known) {
+        CUDA_TRY(e->d_st2_hint.reserve(npairs));
+        CUDA_TRY(cudaMemcpyAsync(e->d_st2_hint.p, hint.data(), sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
     }
-    CUDA_TRY(cudaEventRecord(e->ev1, st));
-    e->timed = true;
-    return BGCA_OK;
+    CUDA_TRY(cudaStreamSynchronize(st));                    // the host vectors above die with this frame
+    return launch_stats2_classes(e, reinterpret_cast<const Stats2Item *>(e->d_st2_items.p), cls_first, e->d_pq.p,
+                                 e->d_ps.p, known ? e->d_st2_hint.p : nullptr, out, st);
+}
+
+// the FP64-compare form of K7 (gotoh_stats2.cuh) serves a batch when every sequence has at most
+// 1023 residues and every DP value stays well inside the +-2^19 its biased score field holds (it
+// does for any protein matrix and gap scores in use)
+static bool stats2_serves(const bgca_engine *e, int longest)
+{
+    const long long worst = 3LL * -e->open + (long long)-e->extend * (2 * longest + 2) +
+                            (long long)e->max_abs_sub * longest + 4096;
+    return longest <= ST2_MAXLEN && worst < (1 << 19) - 4096 && !std::getenv("BGCA_STATS_V1");
 }
 
 int bgca_score_pairs32(bgca_engine *e, const int32_t *pi, const int32_t *pj, int64_t npairs,
@@ -1191,26 +1242,30 @@ try {
     return fail(BGCA_ERR_RANGE, std::string("bgca_score_pairs32: ") + ex.what());
 }
 
-int bgca_pair_stats(bgca_engine *e, const int32_t *pi, const int32_t *pj, int64_t npairs,
-                    bgca_alnstats *out, void *stream)
-try {
-    if (!e || !e->packed || !e->scoring_set) return fail(BGCA_ERR_INVALID, "bgca_pair_stats: pack and set scoring first");
-    if (!pi || !pj || !out || npairs < 0) return fail(BGCA_ERR_INVALID, "bgca_pair_stats: bad arguments");
+static int pair_stats_impl(bgca_engine *e, const int32_t *pi, const int32_t *pj, const int32_t *known_scores,
+                           int64_t npairs, bgca_alnstats *out, void *stream, const char *who)
+{
+    if (!e || !e->packed || !e->scoring_set) return fail(BGCA_ERR_INVALID, std::string(who) + ": pack and set scoring first");
+    if (!pi || !pj || !out || npairs < 0) return fail(BGCA_ERR_INVALID, std::string(who) + ": bad arguments");
     if (npairs == 0) return BGCA_OK;
+    if (npairs > 0x7FFFFFF0) return fail(BGCA_ERR_RANGE, std::string(who) + ": too many pairs for one call");
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(e->device));
     int longest = 0;
     std::vector<int32_t> hq, hs;
-    int rc = stage_pair_list(e, pi, pj, npairs, 32767, "bgca_pair_stats", st, &longest, &hq, &hs);
+    int rc = stage_pair_list(e, pi, pj, npairs, 32767, who, st, &longest, &hq, &hs);
     if (rc != BGCA_OK) return rc;
     // every protein domain fits the one-word tuple; longer sequences take the 96-bit one
     const int compact = (longest <= 1023 && e->max_abs_sub * 1023 < (1 << 21) && -e->open < 1000 && -e->extend < 1000);
-    // ... and the FP64-compare form of it (gotoh_stats2.cuh) when every DP value stays well inside
-    // the +-2^19 its biased score field holds (it does for any protein matrix and gap scores in use)
-    const long long worst = 3LL * -e->open + (long long)-e->extend * (2 * longest + 2) +
-                            (long long)e->max_abs_sub * longest + 4096;
-    if (compact && longest <= ST2_MAXLEN && worst < (1 << 19) - 4096 && !std::getenv("BGCA_STATS_V1"))
-        return run_stats2(e, hq, hs, out, st);
+    if (compact && stats2_serves(e, longest)) {
+        std::vector<int32_t> known;
+        if (known_scores && e->mode == BGCA_MODE_LOCAL) {
+            known.resize(npairs);
+            CUDA_TRY(cudaMemcpyAsync(known.data(), known_scores, sizeof(int32_t) * npairs, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+        }
+        return run_stats2(e, hq, hs, known.empty() ? nullptr : &known, out, st);
+    }
     ScoreParams p;
     fill_params(e, p, nullptr, nullptr, nullptr, 0);
     int max_len = 0;
@@ -1227,8 +1282,111 @@ try {
     e->timed = true;
     e->last_launches = 1;
     return BGCA_OK;
+}
+
+int bgca_pair_stats(bgca_engine *e, const int32_t *pi, const int32_t *pj, int64_t npairs,
+                    bgca_alnstats *out, void *stream)
+try {
+    return pair_stats_impl(e, pi, pj, nullptr, npairs, out, stream, "bgca_pair_stats");
 } catch (const std::exception &ex) {   // std::bad_alloc and friends must not cross the C ABI
     return fail(BGCA_ERR_RANGE, std::string("bgca_pair_stats: ") + ex.what());
+}
+
+int bgca_pair_stats_hinted(bgca_engine *e, const int32_t *pi, const int32_t *pj, const int32_t *known_scores,
+                           int64_t npairs, bgca_alnstats *out, void *stream)
+try {
+    return pair_stats_impl(e, pi, pj, known_scores, npairs, out, stream, "bgca_pair_stats_hinted");
+} catch (const std::exception &ex) {
+    return fail(BGCA_ERR_RANGE, std::string("bgca_pair_stats_hinted: ") + ex.what());
+}
+
+int bgca_select_pairs(bgca_engine *e, const int32_t *scores, int32_t min_score, int32_t same_type_only,
+                      int64_t *count, void *stream)
+try {
+    if (!e || !e->packed || !scores || !count) return fail(BGCA_ERR_INVALID, "bgca_select_pairs: pack first; NULL argument");
+    if (e->n_query != 0 || e->n_db != 0)
+        return fail(BGCA_ERR_INVALID, "bgca_select_pairs: needs one undivided collection (a square score matrix)");
+    if (same_type_only && !e->has_type)
+        return fail(BGCA_ERR_INVALID, "bgca_select_pairs: same_type_only needs type_of_seq at pack time");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(e->device));
+    const int n = e->n;
+    CUDA_TRY(e->d_inv_order.reserve(n));
+    CUDA_TRY(e->d_sel_cnt.reserve(n));
+    CUDA_TRY(e->d_sel_rowstart.reserve((size_t)n + 1));
+    CUDA_TRY(e->d_sel_cls.reserve(3 * 16));                 // [items per class | base per class | fill cursors]
+    CUDA_TRY(cudaMemcpyAsync(e->d_inv_order.p, e->inv_order.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(e->d_sel_cls.p, 0, sizeof(int32_t) * 48, st));
+    CUDA_TRY(launch_select_count(scores, n, min_score, same_type_only ? e->d_type.p : nullptr, e->d_inv_order.p,
+                                 e->d_len.p, kStats2ItemPairs, e->d_sel_cnt.p, e->d_sel_rowstart.p, e->d_sel_cls.p, st));
+    int64_t total = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, e->d_sel_rowstart.p + n, sizeof(total), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(e->sel_cls_items, e->d_sel_cls.p, sizeof(int32_t) * 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (total > 0x7FFFFFF0) return fail(BGCA_ERR_RANGE, "bgca_select_pairs: more than 2^31 pairs selected; raise min_score");
+    e->sel_valid = true;
+    e->sel_min_score = min_score;
+    e->sel_same_type = same_type_only;
+    e->sel_total = total;
+    *count = total;
+    return BGCA_OK;
+} catch (const std::exception &ex) {
+    return fail(BGCA_ERR_RANGE, std::string("bgca_select_pairs: ") + ex.what());
+}
+
+int bgca_pair_stats_selected(bgca_engine *e, const int32_t *scores, int32_t *pairs_out, bgca_alnstats *out,
+                             void *stream)
+try {
+    if (!e || !e->sel_valid || !e->packed) return fail(BGCA_ERR_INVALID, "bgca_pair_stats_selected: call bgca_select_pairs first");
+    if (!scores || !out) return fail(BGCA_ERR_INVALID, "bgca_pair_stats_selected: NULL argument");
+    if (!e->scoring_set) return fail(BGCA_ERR_INVALID, "bgca_pair_stats_selected: call bgca_set_scoring first");
+    e->sel_valid = false;                                   // one selection, one statistics pass
+    const int64_t total = e->sel_total;
+    if (total == 0) return BGCA_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(e->device));
+    const int n = e->n;
+    int longest = 0;
+    for (int r = 0; r < n; ++r) longest = std::max(longest, e->len[r]);
+    if (longest > 32767) return fail(BGCA_ERR_RANGE, "bgca_pair_stats_selected: sequence longer than 32767 residues");
+    const int compact = (longest <= 1023 && e->max_abs_sub * 1023 < (1 << 21) && -e->open < 1000 && -e->extend < 1000);
+    const bool v2 = compact && stats2_serves(e, longest);
+    size_t cls_first[kStats2Classes + 1] = {0};
+    int32_t base[16] = {0};
+    for (int c = 0; c < kStats2Classes; ++c) {
+        base[c] = (int32_t)cls_first[c];
+        cls_first[c + 1] = cls_first[c] + (size_t)e->sel_cls_items[c];
+    }
+    CUDA_TRY(e->d_pq.reserve(total));                       // query of every pair, SORTED index
+    CUDA_TRY(e->d_ps.reserve(total));                       // subject
+    CUDA_TRY(e->d_st2_hint.reserve(total));
+    CUDA_TRY(e->d_st2_items.reserve(std::max<size_t>(cls_first[kStats2Classes], 1) * 4));
+    CUDA_TRY(cudaMemcpyAsync(e->d_sel_cls.p + 16, base, sizeof(int32_t) * 16, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(e->d_sel_cls.p + 32, 0, sizeof(int32_t) * 16, st));
+    CUDA_TRY(launch_select_fill(scores, n, e->sel_min_score, e->sel_same_type ? e->d_type.p : nullptr,
+                                e->d_inv_order.p, e->d_len.p, e->d_sel_rowstart.p, kStats2ItemPairs,
+                                e->d_sel_cls.p + 16, e->d_sel_cls.p + 32, pairs_out, e->d_pq.p, e->d_ps.p,
+                                e->d_st2_hint.p, reinterpret_cast<Stats2Item *>(e->d_st2_items.p), st));
+    if (v2)
+        return launch_stats2_classes(e, reinterpret_cast<const Stats2Item *>(e->d_st2_items.p), cls_first, e->d_ps.p,
+                                     nullptr, e->d_st2_hint.p, out, st);
+    // sequences beyond the compact form: the first K7 kernel over the same device lists
+    ScoreParams p;
+    fill_params(e, p, nullptr, nullptr, nullptr, 0);
+    const int warps_per_cta = CTA_THREADS / 32;
+    int grid = e->n_sm * 4;
+    if ((long long)grid * warps_per_cta > total)
+        grid = (int)std::max<long long>(1, (total + warps_per_cta - 1) / warps_per_cta);
+    const int stride = (longest + 3) & ~3;
+    CUDA_TRY(e->d_scratch_st.reserve((size_t)grid * warps_per_cta * 2 * stride));
+    CUDA_TRY(cudaEventRecord(e->ev0, st));
+    CUDA_TRY(launch_stats(e->mode, compact, p, e->d_pq.p, e->d_ps.p, total, e->d_scratch_st.p, stride, out, grid, st));
+    CUDA_TRY(cudaEventRecord(e->ev1, st));
+    e->timed = true;
+    e->last_launches = 1;
+    return BGCA_OK;
+} catch (const std::exception &ex) {
+    return fail(BGCA_ERR_RANGE, std::string("bgca_pair_stats_selected: ") + ex.what());
 }
 
 int bgca_reduce_bgc(bgca_engine *e, const int32_t *rowbest, const int32_t *selfsc, int64_t *best,

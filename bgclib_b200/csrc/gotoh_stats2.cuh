@@ -15,7 +15,15 @@
 // one DSETP on the FP64 pipe (idle in every other kernel here) plus two selects, instead of two
 // integer compares and two selects on the alu pipe (tools/fp64_probe.cu: 43 vs 28 max/clk/SM).
 // Where only hi changes (E, F) hi itself comes from one DPX VIADDMNMX.  Per cell: 4 DSETP,
-// 7 selects, 2 VIADDMNMX, 1 VIMNMX, 1 ISETP, 5 adds (+ 5 for the running best in local mode).
+// 7 selects, 2 VIADDMNMX, 1 VIMNMX, 1 ISETP, 5 adds (+ 6 for the running best in local mode).
+//
+// HINT (local mode): when the caller knows the best score of every pair — it does whenever the
+// pairs were chosen by score from the scoring kernels' matrix — only cells that reach that score
+// can end the reported alignment.  The running best leaves the hot loop: per four rows one max
+// and one compare against the threshold, and a cold block that does the full lexicographic
+// comparison for the cells that pass (a handful per pair).  A hint that is too low only makes
+// the cold block run more often; one that is too high finds no candidate, which the record
+// shows (score < hint) and the host answers by running the pair again without hints.
 //
 // Layout of the work.  Pairs arrive grouped by query.  A CTA (4 warps) takes a work item = one
 // query and a run of its subjects, builds the query's profile in shared memory —
@@ -54,21 +62,24 @@ struct Stats2Params {
     int32_t n_items;
     int32_t *item_counter;
     const int32_t *subj;       // [npairs] SORTED subject index, grouped by query
-    const int32_t *out_idx;    // [npairs] position of the pair in the caller's list
+    const int32_t *out_idx;    // [npairs] position of the pair in the caller's list (NULL: its own index)
+    const int32_t *hint;       // [npairs] HINT kernels: best local score of the pair, grouped order
+    int32_t *redo_count;       // HINT kernels: pairs whose hint turned out too high
     bgca_alnstats *out;
     int32_t open, extend;
+    int32_t openh, exth;       // open * 1024, extend * 1024: the gap scores in units of hi
     int8_t sub[NSYM * NSYM];
 };
 
 template <int KS>
 struct Stats2Cfg {
-    static constexpr int CH = KS / 4;
+    static constexpr int CH = (KS + 3) / 4;
     static constexpr int LPAD = 32 * KS;
     static constexpr int ROW_BYTES = CH * 32 * 16;
     static constexpr int PROF_BYTES = ST2_PROF_ROWS * ROW_BYTES;
     static constexpr int SLOT_BYTES = ST2_WARPS * 32 * 16;           // per warp a ring of 32 best slots
     static constexpr int SMEM_BYTES = PROF_BYTES + SLOT_BYTES + LPAD + NSYM * NSYM + 16;
-    static constexpr int MIN_CTAS = (KS <= 8) ? 6 : (KS <= 12) ? 5 : (KS <= 16) ? 4 : (KS <= 24) ? 3 : 2;
+    static constexpr int MIN_CTAS = (KS <= 8) ? 6 : (KS <= 12) ? 5 : (KS <= 16) ? 4 : (KS <= 20) ? 3 : 2;
 };
 
 // A DP value lives in a double (the 64-bit word described above, a positive finite number): the
@@ -79,13 +90,14 @@ __device__ __forceinline__ st2_t st2_make(uint32_t hi, uint32_t lo) { return __h
 __device__ __forceinline__ uint32_t st2_hi(st2_t v) { return (uint32_t)__double2hiint(v); }
 __device__ __forceinline__ uint32_t st2_lo(st2_t v) { return (uint32_t)__double2loint(v); }
 
-template <int MODE, int KS>
+template <int MODE, int KS, int HINT = 0>
 __global__ void __launch_bounds__(ST2_THREADS, Stats2Cfg<KS>::MIN_CTAS)
 gotoh_stats2_kernel(const Stats2Params p)
 {
     using Cfg = Stats2Cfg<KS>;
     constexpr int CH = Cfg::CH, LPAD = Cfg::LPAD;
     constexpr bool LOCAL = (MODE == BGCA_MODE_LOCAL);
+    static_assert(!HINT || LOCAL, "score hints only make sense for local alignments");
     constexpr unsigned FULL = 0xFFFFFFFFu;
 
     extern __shared__ uint4 smem_u4[];
@@ -100,7 +112,9 @@ gotoh_stats2_kernel(const Stats2Params p)
     for (int i = tid; i < NSYM * NSYM; i += ST2_THREADS) ssub[i] = p.sub[i];
     for (int i = tid; i < ST2_WARPS * 32; i += ST2_THREADS) slots[i] = make_uint4(0, 0, 0, 0);
 
-    const int EXTH = p.extend * 1024, OPENH = p.open * 1024;       // gap scores in hi units
+    // gap scores in hi units, multiplied on the host: computed here, ptxas folds the shift into
+    // every use as an IMAD and the fused add-max (VIADDMNMX) falls apart into IMAD + VIMNMX
+    const int EXTH = p.exth, OPENH = p.openh;
     const uint32_t prof_lane = (uint32_t)__cvta_generic_to_shared(prof) + (uint32_t)lane * 16u;
     volatile uint4 *const my_slots = slots + warp * 32;
 
@@ -155,10 +169,11 @@ gotoh_stats2_kernel(const Stats2Params p)
         uint32_t off = 0, c = ST2_TOK_IDLE, c1 = ST2_TOK_IDLE;
         // global: Ho / Hoe of the top boundary row H[-1][j] = open + j*ext (lane 0)
         uint32_t top_ho = 0, top_hoe = 0;
+        int thr = 0x7FFFFFFF;                        // HINT: hi of (hinted score, 0 identities)
 
-        auto begin_subject = [&](uint32_t c0, int s) {
+        auto begin_subject = [&](uint32_t c0, int s, int pair) {
             const uint32_t a = prof_lane + c0 * (uint32_t)Cfg::ROW_BYTES;
-            uint32_t P[KS];
+            uint32_t P[CH * 4];
 #pragma unroll
             for (int ch = 0; ch < CH; ++ch) {
                 const uint4 v = *reinterpret_cast<const uint4 *>(__cvta_shared_to_generic(a + ch * 512));
@@ -181,6 +196,7 @@ gotoh_stats2_kernel(const Stats2Params p)
                 }
             }
             best = EMPTY; bend = 0xFFFFFFFFu;
+            if (HINT) thr = (p.hint[pair] + ST2_BIAS) * 1024;
             j = 0;
             Ls_cur = p.seq_len[s];
             top_ho = (uint32_t)((2 * p.open + ST2_BIAS) * 1024);
@@ -193,7 +209,7 @@ gotoh_stats2_kernel(const Stats2Params p)
             c = __ldg(s0);
             c1 = __ldg(s0 + 1);
             off = p.seq_off[s] + 1;
-            begin_subject(c, s);
+            begin_subject(c, s, pair_of(0));
         } else {
 #pragma unroll
             for (int k = 0; k < KS; ++k) { Tn[k] = 0.0; E[k] = 0.0; }
@@ -223,7 +239,7 @@ gotoh_stats2_kernel(const Stats2Params p)
             if (c < ST2_TOK_BOUNDARY) {
                 // ================= hot path: one residue of the current subject ===============
                 const uint32_t a = prof_lane + c1 * (uint32_t)Cfg::ROW_BYTES;    // row of the NEXT token
-                uint32_t P[KS];
+                uint32_t P[CH * 4];
 #pragma unroll
                 for (int ch = 0; ch < CH; ++ch) {
                     uint4 v;
@@ -239,6 +255,7 @@ gotoh_stats2_kernel(const Stats2Params p)
                 const uint32_t z0 = (((uint32_t)(i0 + 1 + j + 1)) << 20) | ((uint32_t)(i0 + 1) << 10) | (uint32_t)(j + 1);
                 const uint32_t cz0 = (uint32_t)(2047 - (i0 + 1 + j + 1)) << 20;
                 const bool last_col = !LOCAL && (j == Ls_cur - 1);
+                uint32_t h4h[4], h4l[4];                           // HINT: the last four rows' H
 #pragma unroll
                 for (int k = 0; k < KS; ++k) {
                     // F[k][j] = max(F[k-1][j] + ext, H[k-1][j] + open): hi by DPX, lo follows the compare
@@ -261,13 +278,32 @@ gotoh_stats2_kernel(const Stats2Params p)
                     const bool pe = E[k] > uhoe;
                     E[k] = st2_make((uint32_t)__viaddmax_s32((int)st2_hi(E[k]), EXTH, (int)uho),
                                     pe ? st2_lo(E[k]) : st2_lo(h));
-                    if (LOCAL) {
+                    if (LOCAL && !HINT) {
                         // running best: strict > keeps the first cell in column-major order, i.e. the
                         // smallest s_end, then the smallest q_end
                         const st2_t cand = st2_make(st2_hi(h), st2_lo(h) + cz0 - (uint32_t)k * (1u << 20));
                         if (cand > best) {
                             best = cand;
                             bend = ((uint32_t)(j + 1) << 16) | (uint32_t)(i0 + k + 1);
+                        }
+                    } else if (LOCAL) {
+                        h4h[k & 3] = st2_hi(h);
+                        h4l[k & 3] = st2_lo(h);
+                        if ((k & 3) == 3 || k == KS - 1) {
+                            const int k0 = k & ~3;
+                            int mx = (int)h4h[0];
+#pragma unroll
+                            for (int r = 1; r <= k - k0; ++r) mx = max(mx, (int)h4h[r]);
+                            if (mx >= thr) {        // cold: some cell of these rows reaches the hinted score
+#pragma unroll
+                                for (int r = 0; r <= k - k0; ++r) {
+                                    const st2_t cand = st2_make(h4h[r], h4l[r] + cz0 - (uint32_t)(k0 + r) * (1u << 20));
+                                    if ((int)h4h[r] >= thr && cand > best) {
+                                        best = cand;
+                                        bend = ((uint32_t)(j + 1) << 16) | (uint32_t)(i0 + k0 + r + 1);
+                                    }
+                                }
+                            }
                         }
                     } else if (last_col) {
                         if (i0 + k == La - 1) cap = h;
@@ -297,6 +333,9 @@ gotoh_stats2_kernel(const Stats2Params p)
                     const int pair = pair_of(ord);
                     bgca_alnstats r;
                     r.score = (int)(rh >> 10) - ST2_BIAS;
+                    if (HINT) {                 // no cell reached the hinted score: the hint was too high
+                        if (r.score < p.hint[pair]) atomicAdd(p.redo_count, 1);
+                    }
                     r.identities = (int)(rh & 1023u);
                     if (LOCAL) {
                         r.columns = 2047 - (int)(rl >> 20);
@@ -316,7 +355,7 @@ gotoh_stats2_kernel(const Stats2Params p)
                         r.q_start = 0; r.s_start = 0; r.q_end = La; r.s_end = Ls;
                         r.gaps = 2 * r.columns - La - Ls;
                     }
-                    p.out[p.out_idx[pair]] = r;
+                    p.out[p.out_idx ? p.out_idx[pair] : pair] = r;
                 }
                 ++ord;
                 if (ord < n_w) {
@@ -325,7 +364,7 @@ gotoh_stats2_kernel(const Stats2Params p)
                     c1 = __ldg(sn);
                     c2 = __ldg(sn + 1);
                     off = p.seq_off[s] + 1;
-                    begin_subject(c1, s);
+                    begin_subject(c1, s, pair_of(ord));
                 } else {
                     c1 = ST2_TOK_IDLE;
                     c2 = ST2_TOK_IDLE;
@@ -340,7 +379,7 @@ gotoh_stats2_kernel(const Stats2Params p)
                     c1 = __ldg(s0);
                     c2 = __ldg(s0 + 1);
                     off = p.seq_off[s] + 1;
-                    begin_subject(c1, s);
+                    begin_subject(c1, s, pair_of(0));
                 }
             }
             __syncwarp();       // slot updates of this step are visible to the lanes that follow

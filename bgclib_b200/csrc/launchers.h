@@ -42,10 +42,20 @@ cudaError_t launch_stats(int mode, int compact, const ScoreParams &p, const int3
                          int grid, cudaStream_t st);
 
 // K7 second form (stats2.cu): sequences of at most 1023 residues, pairs grouped by query
-#define BGCA_STATS2_KS_LIST 4, 8, 12, 16, 24, 32
+#define BGCA_STATS2_KS_LIST 4, 6, 8, 10, 12, 14, 16, 20, 24, 28, 32
 struct Stats2Params;
+struct Stats2Item;
 int stats2_rows_per_lane(int La);
 cudaError_t launch_stats2(int mode, int KS, const Stats2Params &p, int n_sm, cudaStream_t st);
+// pair selection by score on the device (stats2.cu)
+cudaError_t launch_select_count(const int32_t *scores, int n, int min_score, const int32_t *type_sorted,
+                                const int32_t *inv, const int32_t *len_sorted, int item_pairs, int32_t *cnt,
+                                int64_t *row_start, int32_t *cls_items, cudaStream_t st);
+cudaError_t launch_select_fill(const int32_t *scores, int n, int min_score, const int32_t *type_sorted,
+                               const int32_t *inv, const int32_t *len_sorted, const int64_t *row_start,
+                               int item_pairs, const int32_t *cls_base, int32_t *cls_fill, int32_t *pairs_out,
+                               int32_t *q_sorted, int32_t *s_sorted, int32_t *hint, Stats2Item *items,
+                               cudaStream_t st);
 
 // K1 / K5 kernels (pack_reduce.cu)
 cudaError_t launch_pack(const uint8_t *ascii, const int64_t *src_off_sorted, const int32_t *order,

@@ -32,7 +32,8 @@ _lib = None
 EXPORTED_SYMBOLS = (
     "bgca_version", "bgca_last_error", "bgca_create", "bgca_destroy", "bgca_set_scoring",
     "bgca_pack", "bgca_pack_append", "bgca_packed_bytes", "bgca_get_packed", "bgca_plan", "bgca_plan_host",
-    "bgca_score", "bgca_score_pairs32", "bgca_pair_stats", "bgca_reduce_bgc", "bgca_score_all_host",
+    "bgca_score", "bgca_score_pairs32", "bgca_pair_stats", "bgca_pair_stats_hinted", "bgca_select_pairs",
+    "bgca_pair_stats_selected", "bgca_reduce_bgc", "bgca_score_all_host",
     "bgca_last_launches", "bgca_last_dp_ms", "bgca_last_pack_ms", "bgca_dpx_probe",
 )
 
@@ -82,6 +83,9 @@ def load_library():
     lib.bgca_score.argtypes = [vp, vp, vp, vp, i32, vp]
     lib.bgca_score_pairs32.argtypes = [vp, vp, vp, i64, vp, vp]
     lib.bgca_pair_stats.argtypes = [vp, vp, vp, i64, vp, vp]
+    lib.bgca_pair_stats_hinted.argtypes = [vp, vp, vp, vp, i64, vp, vp]
+    lib.bgca_select_pairs.argtypes = [vp, vp, i32, i32, P(i64), vp]
+    lib.bgca_pair_stats_selected.argtypes = [vp, vp, vp, vp, vp]
     lib.bgca_reduce_bgc.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.bgca_score_all_host.argtypes = [vp, vp, vp, i32, vp]
     lib.bgca_last_launches.argtypes = [vp]
@@ -307,10 +311,11 @@ class Engine:
                                                 self._stream()))
         return out
 
-    def pair_stats(self, pi, pj):
+    def pair_stats(self, pi, pj, known_scores=None):
         """K7: alignment statistics without traceback for pairs (query pi[p], subject pj[p]) of the
         packed batch, ORIGINAL indices.  Returns a CUDA int32 tensor [npairs, 8] whose columns are
-        ``ALNSTAT_FIELDS`` (the bgca_alnstats record)."""
+        ``ALNSTAT_FIELDS`` (the bgca_alnstats record).  ``known_scores``: the pairs' alignment
+        scores when the caller has them (local mode: a faster kernel; the result is exact anyway)."""
         t = self.torch
         pi = t.as_tensor(pi, dtype=t.int32, device=self.tdev).contiguous()
         pj = t.as_tensor(pj, dtype=t.int32, device=self.tdev).contiguous()
@@ -318,9 +323,35 @@ class Engine:
             raise ValueError("pi and pj must be 1-D and of equal length")
         out = t.zeros((pi.numel(), len(ALNSTAT_FIELDS)), dtype=t.int32, device=self.tdev)
         with t.cuda.device(self.tdev):
-            _check(self._lib.bgca_pair_stats(self._h, _t_ptr(pi), _t_ptr(pj), pi.numel(), _t_ptr(out),
-                                             self._stream()))
+            if known_scores is None:
+                _check(self._lib.bgca_pair_stats(self._h, _t_ptr(pi), _t_ptr(pj), pi.numel(), _t_ptr(out),
+                                                 self._stream()))
+            else:
+                ks = t.as_tensor(known_scores, dtype=t.int32, device=self.tdev).contiguous()
+                if ks.shape != pi.shape:
+                    raise ValueError("known_scores must have one entry per pair")
+                _check(self._lib.bgca_pair_stats_hinted(self._h, _t_ptr(pi), _t_ptr(pj), _t_ptr(ks), pi.numel(),
+                                                        _t_ptr(out), self._stream()))
         return out
+
+    def pair_stats_above(self, scores, min_score: int, same_type_only: bool = False):
+        """Statistics for every pair i < j of the packed batch whose entry in ``scores`` (the CUDA
+        int32 [n, n] matrix ``score()`` filled) reaches ``min_score``, selected on the device.
+        Returns (pairs int32 [m, 2], stats int32 [m, 8]) as CUDA tensors, pairs in row-major order."""
+        t = self.torch
+        if scores.dtype != t.int32 or not scores.is_cuda or not scores.is_contiguous() or \
+                tuple(scores.shape) != (self.n, self.n):
+            raise ValueError(f"scores must be a contiguous CUDA int32 tensor of shape {(self.n, self.n)}")
+        count = ctypes.c_int64(0)
+        with t.cuda.device(self.tdev):
+            _check(self._lib.bgca_select_pairs(self._h, _t_ptr(scores), int(min_score), int(same_type_only),
+                                               ctypes.byref(count), self._stream()))
+            m = int(count.value)
+            pairs = t.empty((m, 2), dtype=t.int32, device=self.tdev)
+            out = t.zeros((m, len(ALNSTAT_FIELDS)), dtype=t.int32, device=self.tdev)
+            _check(self._lib.bgca_pair_stats_selected(self._h, _t_ptr(scores), _t_ptr(pairs) if m else None,
+                                                      _t_ptr(out) if m else ctypes.c_void_p(8), self._stream()))
+        return pairs, out
 
     def reduce_bgc(self, rowbest, selfsc):
         t = self.torch

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define BGCA_VERSION 104
+#define BGCA_VERSION 105
 
 #define BGCA_MODE_LOCAL 0  /* Smith-Waterman/Gotoh, result = best cell, >= 0        */
 #define BGCA_MODE_GLOBAL 1 /* Needleman-Wunsch/Gotoh, end gaps cost like internal   */
@@ -176,6 +176,26 @@ typedef struct bgca_alnstats {
 } bgca_alnstats;
 int bgca_pair_stats(bgca_engine *e, const int32_t *pi, const int32_t *pj, int64_t npairs,
                     bgca_alnstats *out, void *stream);
+
+/* The same with the best score of every pair known (known_scores[p], device, what bgca_score()
+ * wrote for the pair): in local mode the running best leaves the DP inner loop and only cells
+ * that reach the known score are examined.  The result is exact whatever the hints are — a hint
+ * that is too low costs time, one that is too high is detected and the list is run again without
+ * hints.  Global mode ignores the hints. */
+int bgca_pair_stats_hinted(bgca_engine *e, const int32_t *pi, const int32_t *pj, const int32_t *known_scores,
+                           int64_t npairs, bgca_alnstats *out, void *stream);
+
+/* Statistics for the pairs that are similar at all, chosen ON THE DEVICE from the score matrix
+ * bgca_score() filled (device, int32[n*n], ORIGINAL index space; one undivided collection):
+ * every pair i < j with scores[i][j] >= min_score [and the same domain type], in row-major
+ * order.  bgca_select_pairs() counts them (*count; the caller sizes its outputs);
+ * bgca_pair_stats_selected() then writes pairs_out[count][2] = (i, j) (device, nullable) and
+ * out[count] (device) in that order, with the selected scores as hints.  The pair list never
+ * visits the host.  One selection serves one statistics pass. */
+int bgca_select_pairs(bgca_engine *e, const int32_t *scores, int32_t min_score, int32_t same_type_only,
+                      int64_t *count, void *stream);
+int bgca_pair_stats_selected(bgca_engine *e, const int32_t *scores, int32_t *pairs_out, bgca_alnstats *out,
+                             void *stream);
 
 /* K5 second stage (after ranks combined rowbest/selfsc with max):
  *   best[a,b] = sum_{d in a} rowbest[d,b]   int64[n_bgc*n_bgc]

@@ -740,6 +740,61 @@ def test_stats_for_pairs_above_a_score():
     assert (res.stats["score"] >= thr).all()
 
 
+def test_stats_with_known_scores_right_low_and_high():
+    """bgca_pair_stats_hinted: with the true scores as hints, with hints that are too low (more
+    candidate cells, same answer) and with hints that are too high (no candidate -> detected, run
+    again without hints) the records equal the oracle's; global mode ignores hints."""
+    rng = np.random.default_rng(31)
+    seqs = _related(rng, 5, 6, 40, 520) + [_rand(rng, k) for k in (1, 2, 33, 129, 257, 385, 449, 513, 1023)]
+    n = len(seqs)
+    iu = np.triu_indices(n, k=0)
+    pi, pj = iu[0].astype(np.int32), iu[1].astype(np.int32)
+    eng = get_engine()
+    for mode, cm in (("local", oracle.MODE_LOCAL), ("global", oracle.MODE_GLOBAL)):
+        eng.set_scoring("BLOSUM62", -12, -1, mode)
+        eng.pack(seqs)
+        want = oracle.stats_list(seqs, pi, pj, mode=cm)
+        true = want["score"].astype(np.int32)
+        for hints in (true, np.maximum(true - rng.integers(0, 40, len(true)).astype(np.int32), 0),
+                      true + (rng.random(len(true)) < 0.05) * 7, np.zeros_like(true)):
+            got = eng.pair_stats(pi, pj, known_scores=hints.astype(np.int32)).cpu().numpy()
+            got = np.ascontiguousarray(got).view(oracle.STATS_DTYPE).reshape(-1)
+            assert (_stat_rows(got) == _stat_rows(want)).all(), mode
+
+
+@pytest.mark.parametrize("same_type_only", [False, True])
+def test_stats_selected_on_the_device(same_type_only):
+    """bgca_select_pairs + bgca_pair_stats_selected: pairs i < j above a score chosen on the device
+    from the score matrix (row-major order, optional same-type restriction), statistics with the
+    selected scores as hints; pairs and records equal the oracle's, in both modes."""
+    import torch
+    rng = np.random.default_rng(33 + same_type_only)
+    seqs = _related(rng, 6, 7, 50, 500) + [_rand(rng, k) for k in (30, 90, 300, 700)]
+    n = len(seqs)
+    types = rng.integers(0, 3, n).astype(np.int32)
+    eng = get_engine()
+    for mode, cm, thr in (("local", oracle.MODE_LOCAL, 90), ("global", oracle.MODE_GLOBAL, -400)):
+        eng.set_scoring("BLOSUM62", -12, -1, mode)
+        eng.pack(seqs, type_of_seq=types if same_type_only else None)
+        eng.plan(same_type_only=same_type_only)
+        scores = torch.full((n, n), -2**31, dtype=torch.int32, device="cuda")
+        eng.score(scores=scores)
+        pairs, out = eng.pair_stats_above(scores, thr, same_type_only)
+        full = oracle.all_pairs(seqs, mode=cm)
+        keep = np.triu(full >= thr, k=1)
+        if same_type_only:
+            keep &= types[:, None] == types[None, :]
+        want_pairs = np.argwhere(keep)
+        assert 0 < len(want_pairs) < n * (n - 1) // 2
+        assert (pairs.cpu().numpy() == want_pairs).all()
+        want = oracle.stats_list(seqs, want_pairs[:, 0], want_pairs[:, 1], mode=cm)
+        got = np.ascontiguousarray(out.cpu().numpy()).view(oracle.STATS_DTYPE).reshape(-1)
+        assert (_stat_rows(got) == _stat_rows(want)).all(), mode
+    # nothing above the threshold: empty result, and the selection is spent
+    pairs, out = eng.pair_stats_above(scores, 10**6, same_type_only)
+    assert pairs.shape == (0, 2) and out.shape[0] == 0
+
+
 def test_outputs_stay_inside_their_buffers():
     """Guard rows around every caller-owned output (compute-sanitizer is not available on the
     pool): nothing outside the declared shapes may be written, whatever the kernel variant."""

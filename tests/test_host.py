@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     lib = eng.load_library()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.bgca_version() == 104
+    assert lib.bgca_version() == 105
 
 
 def test_no_device_fails_loudly():
