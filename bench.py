@@ -480,7 +480,7 @@ def main():
         eng.pack_ascii(col.ascii, col.offsets)                 # leave the engine on the bench workload
 
     # ---- fused BGC similarity, strong scaling on one fixed collection (configs[3]; [4] at N = 8) ----
-    fused = fused5 = None
+    fused = fused5 = api_e2e = None
     if not args.no_fused:
         from bgclib_b200 import synth as _synth
         col4 = _synth.mibig_scale(2500)
@@ -500,6 +500,32 @@ def main():
                                                      "oracle.all_pairs + oracle.bgc_similarity_np on rank 0"}
             parity["pairs"] += 300 * 301 // 2
             parity["mismatches"] += bad
+        # ---- the same collection as OBJECTS through the public Python API (N = 1): how much of
+        # bgc_similarity(collection) is spent outside the DP kernels (extraction + pack) ----------
+        if world == 1:
+            import time as _t
+            from bgclib_b200 import api as _api, extract as _extract
+            objs = _synth.as_collection(col4)
+            t0 = _t.perf_counter()
+            batch = _extract(objs)
+            t_extract = _t.perf_counter() - t0
+            torch.cuda.synchronize()
+            t0 = _t.perf_counter()
+            eng.pack_batch(batch, type_of_seq=batch.type_of_seq, bgc_of_seq=batch.bgc_of_seq, n_bgc=len(batch.bgc_ids))
+            torch.cuda.synchronize()
+            t_pack = _t.perf_counter() - t0
+            t0 = _t.perf_counter()
+            res = _api.bgc_similarity(objs, device=local_rank)          # host objects in, host matrices out
+            torch.cuda.synchronize()
+            t_call = _t.perf_counter() - t0
+            api_e2e = {"api": "bgclib_b200.bgc_similarity(collection of BGC/protein/domain objects) -> numpy sim, best, self",
+                       "workload": f"{len(batch)} domains on {sum(len(g.protein_list) for g in objs.bgcs.values())} "
+                                   f"proteins in {len(objs.bgcs)} BGCs (configs[3] as objects)",
+                       "call_s": t_call, "gcups": fused["cells"] / t_call / 1e9,
+                       "extract_s": t_extract, "pack_s": t_pack, "extract_plus_pack_share": (t_extract + t_pack) / t_call,
+                       "residue_buffer_bytes": int(batch.spans()[0].nbytes),
+                       "sim_shape": list(res.sim.shape), "sim_diag_ones": bool((np.diag(res.sim) == 1).all())}
+            del objs, batch, res
         del col4
         if args.fused_config5 or world >= 8:
             col5 = _synth.nrps_pks_100k(4167)
@@ -572,7 +598,7 @@ def main():
             "pairs_per_s": total_pairs / (ms_per_step * 1e-3),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu, "hbm_stages": stages,
-            "fused": fused, "fused_config5": fused5, "parity_sample": parity,
+            "fused": fused, "fused_config5": fused5, "api_e2e": api_e2e, "parity_sample": parity,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

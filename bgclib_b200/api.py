@@ -97,8 +97,9 @@ def _as_batch(source, unit, cbp_only, alias, domain_types) -> DomainBatch:
 
 
 def _merge(q: DomainBatch, d: DomainBatch):
-    """Query batch followed by database batch: one sequence list, a shared type-id space and
-    the BGC index space [query BGCs | database BGCs] (ids are NOT merged across the two sides)."""
+    """Query batch followed by database batch: one span list over the two residue buffers laid end
+    to end, a shared type-id space and the BGC index space [query BGCs | database BGCs] (ids are
+    NOT merged across the two sides).  Returns ((blob, starts, lengths), types, bgcs)."""
     type_names = list(q.type_names)
     pos = {t: i for i, t in enumerate(type_names)}
     for t in d.type_names:
@@ -108,7 +109,9 @@ def _merge(q: DomainBatch, d: DomainBatch):
     d_types = np.asarray([pos[t] for t in d.type_names], dtype=np.int32)
     types = np.concatenate([q.type_of_seq, d_types[d.type_of_seq] if len(d) else d.type_of_seq]).astype(np.int32)
     bgcs = np.concatenate([q.bgc_of_seq, d.bgc_of_seq + len(q.bgc_ids)]).astype(np.int32)
-    return q.sequences + d.sequences, types, bgcs
+    (qb, qs, ql), (db, ds, dl) = q.spans(), d.spans()
+    spans = (np.concatenate([qb, db]), np.concatenate([qs, ds + len(qb)]), np.concatenate([ql, dl]))
+    return spans, types, bgcs
 
 
 def domain_pair_scores(source, *, database=None, mode="local", matrix="BLOSUM62", open_gap_score=-12,
@@ -158,12 +161,12 @@ def domain_pair_scores(source, *, database=None, mode="local", matrix="BLOSUM62"
         db = _as_batch(database, unit, cbp_only, alias, domain_types)
         if len(db) == 0:
             raise ValueError("no domain sequences selected in the database")
-        seqs, types, _ = _merge(batch, db)
-        eng.pack(seqs, type_of_seq=types if same_type_only else None, n_query=n)
+        spans, types, _ = _merge(batch, db)
+        eng.pack_spans(*spans, type_of_seq=types if same_type_only else None, n_query=n)
         plan = eng.plan(same_type_only=same_type_only, rank=rank, world=world, cross_only=True)
         ncols = len(db)
     else:
-        eng.pack(batch.sequences, type_of_seq=batch.type_of_seq if same_type_only else None)
+        eng.pack_batch(batch, type_of_seq=batch.type_of_seq if same_type_only else None)
         plan = eng.plan(same_type_only=same_type_only, rank=rank, world=world)
         ncols = n
     rows = (0, n) if shard_rows else None      # a single process holds every row
@@ -249,7 +252,7 @@ def bgc_similarity(source, *, database=None, matrix="BLOSUM62", open_gap_score=-
         return BGCSimilarity(z, z.astype(np.int64), np.zeros(B, np.int64), ids, [], {})
     eng.set_scoring(matrix, open_gap_score, extend_gap_score, "local")
     dist, rank, world = _dist()
-    eng.pack(batch.sequences, type_of_seq=batch.type_of_seq, bgc_of_seq=bgc_of, n_bgc=B)
+    eng.pack_batch(batch, type_of_seq=batch.type_of_seq, bgc_of_seq=bgc_of, n_bgc=B)
     rowbest = torch.zeros((n, B), dtype=torch.int32, device=eng.tdev)
     selfsc = torch.zeros((n,), dtype=torch.int32, device=eng.tdev)
     rounds = max(1, int(rounds))
@@ -293,7 +296,7 @@ class _Checkpoint:
         from pathlib import Path
         self.path = Path(f"{path}.rank{rank}.npz")
         h = hashlib.sha256()
-        h.update("\x00".join(batch.sequences).encode("ascii"))
+        batch.digest_update(h)
         h.update(np.ascontiguousarray(bgc_of, dtype=np.int32).tobytes())
         h.update(np.ascontiguousarray(batch.type_of_seq, dtype=np.int32).tobytes())
         h.update(np.ascontiguousarray(np.asarray(matrix) if not isinstance(matrix, str) else
@@ -326,14 +329,14 @@ def _bgc_similarity_cross(q: DomainBatch, d: DomainBatch, matrix, open_gap_score
     Bq, Bd = len(q.bgc_ids), len(d.bgc_ids)
     if Bq == 0 or Bd == 0 or len(q) == 0 or len(d) == 0:
         raise ValueError("query and database must both hold BGCs with domain sequences")
-    seqs, types, bgcs = _merge(q, d)
-    n, B = len(seqs), Bq + Bd
+    spans, types, bgcs = _merge(q, d)
+    n, B = len(q) + len(d), Bq + Bd
     eng = get_engine(device)
     torch = eng.torch
     eng.set_scoring(matrix, open_gap_score, extend_gap_score, "local")
     dist, rank, world = _dist()
     # the packer sorts by (type, role, length): without types the single block is [queries | database]
-    eng.pack(seqs, type_of_seq=types if same_type_only else None, bgc_of_seq=bgcs, n_bgc=B, n_query=len(q))
+    eng.pack_spans(*spans, type_of_seq=types if same_type_only else None, bgc_of_seq=bgcs, n_bgc=B, n_query=len(q))
     plan = eng.plan(same_type_only=same_type_only, rank=rank, world=world, cross_only=True)
     rowbest = torch.zeros((n, B), dtype=torch.int32, device=eng.tdev)
     selfsc = torch.zeros((n,), dtype=torch.int32, device=eng.tdev)
@@ -374,8 +377,8 @@ class PackedDatabase:
         self.scoring = (matrix, int(open_gap_score), int(extend_gap_score))
         eng = self.engine
         eng.set_scoring(matrix, open_gap_score, extend_gap_score, "local")
-        eng.pack(self.batch.sequences, type_of_seq=self.batch.type_of_seq, bgc_of_seq=self.batch.bgc_of_seq,
-                 n_bgc=len(self.batch.bgc_ids))
+        eng.pack_batch(self.batch, type_of_seq=self.batch.type_of_seq, bgc_of_seq=self.batch.bgc_of_seq,
+                       n_bgc=len(self.batch.bgc_ids))
         # self scores of the database domains, once (the similarity is normalised with them)
         idx = torch.arange(len(self.batch), dtype=torch.int32, device=eng.tdev)
         self.selfsc = eng.score_pairs32(idx, idx)
@@ -484,7 +487,7 @@ def domain_pair_stats(source, pairs=None, *, mode="local", matrix="BLOSUM62", op
         raise ValueError("pairs: index out of range")
     eng = get_engine(device)
     eng.set_scoring(matrix, open_gap_score, extend_gap_score, mode)
-    eng.pack(batch.sequences)
+    eng.pack_batch(batch)
     if dist is None:
         out = eng.pair_stats(pairs[:, 0].copy(), pairs[:, 1].copy())
     else:

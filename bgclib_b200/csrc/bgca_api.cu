@@ -540,11 +540,13 @@ int bgca_set_scoring(bgca_engine *e, const int8_t *sub, int32_t open, int32_t ex
     return BGCA_OK;
 }
 
-int bgca_pack(bgca_engine *e, const uint8_t *ascii, const int64_t *offsets, int32_t n,
-              const int32_t *type_of_seq, const int32_t *bgc_of_seq, int32_t n_bgc,
-              int32_t n_query, int32_t ascii_on_device, void *stream)
-try {
-    if (!e || !ascii || !offsets) return fail(BGCA_ERR_INVALID, "bgca_pack: NULL argument");
+// Shared body of bgca_pack / bgca_pack_spans: sequence i is ascii[src_off[i], src_off[i] + src_len[i])
+// of a buffer of ascii_bytes bytes (host or device).  Sequences may overlap or leave gaps — domains
+// are slices of their proteins' sequences.
+static int pack_impl(bgca_engine *e, const uint8_t *ascii, int64_t ascii_bytes, const int64_t *src_off,
+                     const int64_t *src_len, int32_t n, const int32_t *type_of_seq, const int32_t *bgc_of_seq,
+                     int32_t n_bgc, int32_t n_query, int32_t ascii_on_device, void *stream)
+{
     if (n <= 0) return fail(BGCA_ERR_INVALID, "bgca_pack: need at least one sequence");
     if (bgc_of_seq && (n_bgc <= 0 || n_bgc > 65535))
         return fail(BGCA_ERR_RANGE, "bgca_pack: n_bgc must be in 1..65535");
@@ -557,8 +559,10 @@ try {
 
     std::vector<int32_t> len_orig(n);
     for (int i = 0; i < n; ++i) {
-        const int64_t l = offsets[i + 1] - offsets[i];
+        const int64_t l = src_len[i];
         if (l < 0) return fail(BGCA_ERR_INVALID, "bgca_pack: offsets must be non-decreasing");
+        if (src_off[i] < 0 || src_off[i] + l > ascii_bytes)
+            return fail(BGCA_ERR_INVALID, "sequence " + std::to_string(i) + " lies outside the residue buffer");
         if (l == 0) return fail(BGCA_ERR_EMPTY, "sequence " + std::to_string(i) + " has zero length");
         if (l > 65535) return fail(BGCA_ERR_RANGE, "sequence " + std::to_string(i) + " longer than 65535");
         len_orig[i] = (int32_t)l;
@@ -613,17 +617,16 @@ try {
         for (int i = 0; i < n; ++i) e->bgc_doms[cur[bgc_of_seq[i]]++] = i;
     }
 
-    const int64_t total_ascii = offsets[n] - offsets[0];
-    const uint8_t *d_src = ascii + offsets[0];
+    const uint8_t *d_src = ascii;
     if (!ascii_on_device) {
-        CUDA_TRY(e->d_ascii.reserve((size_t)total_ascii + 16));   // K1 reads whole aligned 16-byte words
-        CUDA_TRY(cudaMemcpyAsync(e->d_ascii.p, ascii + offsets[0], (size_t)total_ascii,
-                                 cudaMemcpyHostToDevice, st));
+        CUDA_TRY(e->d_ascii.reserve((size_t)ascii_bytes + 16));   // K1 reads whole aligned 4-byte words
+        if (ascii_bytes > 0)
+            CUDA_TRY(cudaMemcpyAsync(e->d_ascii.p, ascii, (size_t)ascii_bytes, cudaMemcpyHostToDevice, st));
         d_src = e->d_ascii.p;
     }
     // source byte offset of every SORTED sequence (relative to d_src): one gather less on the device
     std::vector<int64_t> off_rel(n);
-    for (int r = 0; r < n; ++r) off_rel[r] = offsets[e->order[r]] - offsets[0];
+    for (int r = 0; r < n; ++r) off_rel[r] = src_off[e->order[r]];
     CUDA_TRY(e->d_offsets_orig.reserve(n));
     CUDA_TRY(e->d_order.reserve(n));
     CUDA_TRY(e->d_len.reserve(n));
@@ -661,8 +664,38 @@ try {
     }
     e->packed = true;
     return BGCA_OK;
+}
+
+int bgca_pack(bgca_engine *e, const uint8_t *ascii, const int64_t *offsets, int32_t n,
+              const int32_t *type_of_seq, const int32_t *bgc_of_seq, int32_t n_bgc,
+              int32_t n_query, int32_t ascii_on_device, void *stream)
+try {
+    if (!e || !ascii || !offsets) return fail(BGCA_ERR_INVALID, "bgca_pack: NULL argument");
+    if (n <= 0) return fail(BGCA_ERR_INVALID, "bgca_pack: need at least one sequence");
+    std::vector<int64_t> off(n), len(n);
+    for (int i = 0; i < n; ++i) {
+        off[i] = offsets[i] - offsets[0];
+        len[i] = offsets[i + 1] - offsets[i];
+    }
+    return pack_impl(e, ascii + offsets[0], offsets[n] - offsets[0], off.data(), len.data(), n, type_of_seq,
+                     bgc_of_seq, n_bgc, n_query, ascii_on_device, stream);
 } catch (const std::exception &ex) {   // std::bad_alloc and friends must not cross the C ABI
     return fail(BGCA_ERR_RANGE, std::string("bgca_pack: ") + ex.what());
+}
+
+int bgca_pack_spans(bgca_engine *e, const uint8_t *ascii, int64_t ascii_bytes, const int64_t *span_start,
+                    const int32_t *span_len, int32_t n, const int32_t *type_of_seq, const int32_t *bgc_of_seq,
+                    int32_t n_bgc, int32_t n_query, int32_t ascii_on_device, void *stream)
+try {
+    if (!e || !ascii || !span_start || !span_len || ascii_bytes < 0)
+        return fail(BGCA_ERR_INVALID, "bgca_pack_spans: NULL argument");
+    if (n <= 0) return fail(BGCA_ERR_INVALID, "bgca_pack_spans: need at least one sequence");
+    std::vector<int64_t> len(n);
+    for (int i = 0; i < n; ++i) len[i] = span_len[i];
+    return pack_impl(e, ascii, ascii_bytes, span_start, len.data(), n, type_of_seq, bgc_of_seq, n_bgc, n_query,
+                     ascii_on_device, stream);
+} catch (const std::exception &ex) {
+    return fail(BGCA_ERR_RANGE, std::string("bgca_pack_spans: ") + ex.what());
 }
 
 int bgca_pack_append(bgca_engine *e, const uint8_t *ascii, const int64_t *offsets, int32_t n_new,

@@ -31,7 +31,7 @@ _lib = None
 # every symbol include/bgca.h declares (tests check the library exports them all)
 EXPORTED_SYMBOLS = (
     "bgca_version", "bgca_last_error", "bgca_create", "bgca_destroy", "bgca_set_scoring",
-    "bgca_pack", "bgca_pack_append", "bgca_packed_bytes", "bgca_get_packed", "bgca_plan", "bgca_plan_host",
+    "bgca_pack", "bgca_pack_spans", "bgca_pack_append", "bgca_packed_bytes", "bgca_get_packed", "bgca_plan", "bgca_plan_host",
     "bgca_score", "bgca_score_pairs32", "bgca_pair_stats", "bgca_pair_stats_hinted", "bgca_select_pairs",
     "bgca_pair_stats_selected", "bgca_reduce_bgc", "bgca_score_all_host",
     "bgca_last_launches", "bgca_last_dp_ms", "bgca_last_pack_ms", "bgca_dpx_probe",
@@ -73,6 +73,7 @@ def load_library():
     lib.bgca_destroy.argtypes = [vp]
     lib.bgca_set_scoring.argtypes = [vp, vp, i32, i32, i32]
     lib.bgca_pack.argtypes = [vp, vp, vp, i32, vp, vp, i32, i32, i32, vp]
+    lib.bgca_pack_spans.argtypes = [vp, vp, i64, vp, vp, i32, vp, vp, i32, i32, i32, vp]
     lib.bgca_pack_append.argtypes = [vp, vp, vp, i32, vp, vp, i32, i32, vp]
     lib.bgca_packed_bytes.argtypes = [vp]
     lib.bgca_packed_bytes.restype = i64
@@ -244,6 +245,42 @@ class Engine:
         self.cross = False
         self.n_bgc = int(n_bgc) if bgcs is not None else 0
         self.plan_info = None
+
+    def pack_spans(self, blob, starts, lengths, type_of_seq=None, bgc_of_seq=None, n_bgc: int = 0, n_query: int = 0):
+        """Sequences given as slices of one residue buffer (``DomainBatch.spans()``): sequence i =
+        blob[starts[i] : starts[i] + lengths[i]].  blob: uint8 numpy array (host) or torch uint8 CUDA
+        tensor; starts int64[n], lengths int32[n] host.  The slices are cut by K1 on the device."""
+        starts = np.ascontiguousarray(starts, dtype=np.int64)
+        lengths = np.ascontiguousarray(lengths, dtype=np.int32)
+        n = len(starts)
+        if len(lengths) != n:
+            raise ValueError("starts and lengths must have one entry per sequence")
+        types = None if type_of_seq is None else np.ascontiguousarray(type_of_seq, dtype=np.int32)
+        bgcs = None if bgc_of_seq is None else np.ascontiguousarray(bgc_of_seq, dtype=np.int32)
+        for a in (types, bgcs):
+            if a is not None and len(a) != n:
+                raise ValueError("type_of_seq / bgc_of_seq must have one entry per sequence")
+        on_device = not isinstance(blob, np.ndarray)
+        if on_device:
+            if blob.dtype != self.torch.uint8 or not blob.is_cuda:
+                raise ValueError("device blob must be a CUDA uint8 tensor")
+            blob = blob.contiguous()
+            ptr, nbytes = _t_ptr(blob), int(blob.numel())
+        else:
+            blob = np.ascontiguousarray(blob, dtype=np.uint8)
+            ptr, nbytes = (_np_ptr(blob) if blob.size else ctypes.c_void_p(1)), int(blob.size)
+        with self.torch.cuda.device(self.tdev):
+            _check(self._lib.bgca_pack_spans(self._h, ptr, nbytes, _np_ptr(starts), _np_ptr(lengths), n, _np_ptr(types),
+                                             _np_ptr(bgcs), int(n_bgc), int(n_query), int(on_device), self._stream()))
+        self.n = n
+        self.n_query = int(n_query)
+        self.cross = False
+        self.n_bgc = int(n_bgc) if bgcs is not None else 0
+        self.plan_info = None
+
+    def pack_batch(self, batch, type_of_seq=None, bgc_of_seq=None, n_bgc: int = 0, n_query: int = 0):
+        """A DomainBatch through its span form: no per-domain Python strings on the way to K1."""
+        return self.pack_spans(*batch.spans(), type_of_seq, bgc_of_seq, n_bgc, n_query)
 
     def pack_append(self, seqs: Sequence[str], type_of_seq=None, bgc_of_seq=None, n_bgc_total: int = 0):
         """Append a query set behind the batch packed earlier (which stays resident as the database);

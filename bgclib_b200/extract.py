@@ -17,7 +17,7 @@ Reference contract followed:
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Iterable, List, Optional, Sequence
 
 import numpy as np
@@ -36,18 +36,81 @@ class DomainRecord:
     length: int
 
 
-@dataclass
 class DomainBatch:
-    sequences: List[str]
-    records: List[DomainRecord]
-    bgc_ids: List[str]                     # row/column identity of the BGC matrix
-    bgc_of_seq: np.ndarray                 # int32[n]
-    type_names: List[str]
-    type_of_seq: np.ndarray                # int32[n]
-    skipped: List[str] = field(default_factory=list)   # human-readable notes (empty domains ...)
+    """The flattened collection the engine packs.  Two interchangeable forms:
+
+    * list form  — ``sequences`` (list of str) and ``records`` given up front (hand-built batches,
+      FASTA input);
+    * array form — what ``extract`` produces: every protein's sequence ONCE in ``blob`` (uint8) and
+      per domain a slice (``starts``, ``lengths``) into it, i.e. ``BGCDomain.get_sequence()``
+      (BGClib/BGClib.py:3240-3241) as numbers instead of 10^5 Python string slices; K1 cuts the
+      slices on the device (``bgca_pack_spans``).  ``sequences`` and ``records`` are then built
+      only when somebody asks for them.
+
+    Either way: ``bgc_ids`` / ``bgc_of_seq`` (row identity of the BGC matrix), ``type_names`` /
+    ``type_of_seq`` (domain type keys), ``skipped`` (human-readable notes: empty domains ...)."""
+
+    def __init__(self, sequences=None, records=None, bgc_ids=None, bgc_of_seq=None, type_names=None,
+                 type_of_seq=None, skipped=None, *, blob=None, starts=None, lengths=None, meta=None):
+        self._sequences = None if sequences is None else list(sequences)
+        self._records = None if records is None else list(records)
+        self.bgc_ids = list(bgc_ids if bgc_ids is not None else [])
+        self.bgc_of_seq = np.asarray(bgc_of_seq if bgc_of_seq is not None else [], dtype=np.int32)
+        self.type_names = list(type_names if type_names is not None else [])
+        self.type_of_seq = np.asarray(type_of_seq if type_of_seq is not None else [], dtype=np.int32)
+        self.skipped = list(skipped) if skipped is not None else []
+        self._blob = None if blob is None else np.ascontiguousarray(blob, dtype=np.uint8)
+        self._starts = None if starts is None else np.ascontiguousarray(starts, dtype=np.int64)
+        self._lengths = None if lengths is None else np.ascontiguousarray(lengths, dtype=np.int32)
+        # array form: (protein identifiers, domain ids, ali_from, ali_to) per domain, for lazy records
+        self._meta = meta
+        if self._sequences is None and self._blob is None:
+            raise ValueError("DomainBatch needs sequences or (blob, starts, lengths)")
 
     def __len__(self):
-        return len(self.sequences)
+        return len(self._sequences) if self._sequences is not None else len(self._lengths)
+
+    # ---- the two views of the residues ----------------------------------------------------------
+    @property
+    def sequences(self) -> List[str]:
+        if self._sequences is None:
+            text = self._blob.tobytes().decode("ascii")
+            self._sequences = [text[a:a + l] for a, l in zip(self._starts.tolist(), self._lengths.tolist())]
+        return self._sequences
+
+    def spans(self):
+        """(blob uint8, starts int64[n], lengths int32[n]): sequence i = blob[starts[i] : starts[i] + lengths[i]]."""
+        if self._blob is None:
+            lens = np.fromiter((len(x) for x in self._sequences), dtype=np.int64, count=len(self._sequences))
+            starts = np.zeros(len(lens), dtype=np.int64)
+            np.cumsum(lens[:-1], out=starts[1:])
+            try:
+                raw = "".join(self._sequences).encode("ascii")
+            except UnicodeEncodeError:
+                raise ValueError("sequences must be ASCII protein letters") from None
+            self._blob = np.frombuffer(raw, dtype=np.uint8) if raw else np.zeros(0, np.uint8)
+            self._starts, self._lengths = starts, lens.astype(np.int32)
+        return self._blob, self._starts, self._lengths
+
+    @property
+    def records(self) -> List["DomainRecord"]:
+        if self._records is None:
+            prot, dom, a0, a1 = self._meta
+            tn, bi = self.type_names, self.bgc_ids
+            self._records = [DomainRecord(i, bi[b], prot[i], dom[i], tn[t], int(a0[i]), int(a1[i]), int(l))
+                             for i, (b, t, l) in enumerate(zip(self.bgc_of_seq.tolist(), self.type_of_seq.tolist(),
+                                                               self._lengths.tolist()))]
+        return self._records
+
+    def digest_update(self, h) -> None:
+        """Feeds the residues (in order, with their boundaries) to a hashlib object."""
+        blob, starts, lengths = self.spans()
+        h.update(np.ascontiguousarray(lengths).tobytes())
+        if len(lengths) and (starts[1:] == starts[:-1] + lengths[:-1]).all() and starts[0] == 0 and \
+                int(starts[-1] + lengths[-1]) == len(blob):
+            h.update(blob.tobytes())                     # contiguous: no copy of the slices needed
+        else:
+            h.update("\x00".join(self.sequences).encode("ascii"))
 
     def select_bgcs(self, ids: Sequence[str]) -> "DomainBatch":
         """The batch restricted to the BGCs named in ``ids``, in that order (the reading a
@@ -56,39 +119,41 @@ class DomainBatch:
         new_of_old = np.full(len(self.bgc_ids), -1, dtype=np.int32)
         for k, b in enumerate(ids):
             new_of_old[pos[b]] = k
-        keep = [i for i in range(len(self.sequences)) if new_of_old[self.bgc_of_seq[i]] >= 0]
-        recs = [DomainRecord(k, *(getattr(self.records[i], f) for f in
+        keep = np.nonzero(new_of_old[self.bgc_of_seq] >= 0)[0] if len(self) else np.zeros(0, np.int64)
+        old = self.records
+        recs = [DomainRecord(k, *(getattr(old[i], f) for f in
                                  ("bgc_id", "protein_identifier", "domain_id", "type_key", "ali_from", "ali_to", "length")))
-                for k, i in enumerate(keep)]
-        return DomainBatch([self.sequences[i] for i in keep], recs, list(ids),
+                for k, i in enumerate(keep.tolist())]
+        seqs = self.sequences
+        return DomainBatch([seqs[i] for i in keep.tolist()], recs, list(ids),
                            new_of_old[self.bgc_of_seq[keep]].astype(np.int32), list(self.type_names),
                            self.type_of_seq[keep].astype(np.int32), list(self.skipped))
 
     # ---- on-disk form (resumable / repeated runs: a database is extracted once) -------------
     def save(self, path) -> None:
         """One .npz: ASCII residues + offsets + type/BGC ids + the identity tables."""
-        offsets = np.zeros(len(self.sequences) + 1, dtype=np.int64)
-        np.cumsum([len(s) for s in self.sequences], out=offsets[1:])
+        seqs = self.sequences
+        offsets = np.zeros(len(seqs) + 1, dtype=np.int64)
+        np.cumsum([len(x) for x in seqs], out=offsets[1:])
+        recs = self.records
         np.savez_compressed(
-            path, ascii=np.frombuffer("".join(self.sequences).encode("ascii"), dtype=np.uint8),
+            path, ascii=np.frombuffer("".join(seqs).encode("ascii"), dtype=np.uint8),
             offsets=offsets, type_of_seq=self.type_of_seq, bgc_of_seq=self.bgc_of_seq,
             type_names=np.asarray(self.type_names, dtype=object), bgc_ids=np.asarray(self.bgc_ids, dtype=object),
-            protein=np.asarray([r.protein_identifier for r in self.records], dtype=object),
-            domain=np.asarray([r.domain_id for r in self.records], dtype=object),
-            ali=np.asarray([[r.ali_from, r.ali_to] for r in self.records], dtype=np.int64).reshape(-1, 2))
+            protein=np.asarray([r.protein_identifier for r in recs], dtype=object),
+            domain=np.asarray([r.domain_id for r in recs], dtype=object),
+            ali=np.asarray([[r.ali_from, r.ali_to] for r in recs], dtype=np.int64).reshape(-1, 2))
 
     @classmethod
     def load(cls, path) -> "DomainBatch":
         z = np.load(path, allow_pickle=True)
-        blob = z["ascii"].tobytes().decode("ascii")
         off = z["offsets"]
-        seqs = [blob[off[i]:off[i + 1]] for i in range(len(off) - 1)]
         type_names, bgc_ids = list(z["type_names"]), list(z["bgc_ids"])
-        recs = [DomainRecord(i, bgc_ids[z["bgc_of_seq"][i]], str(z["protein"][i]), str(z["domain"][i]),
-                             type_names[z["type_of_seq"][i]], int(z["ali"][i][0]), int(z["ali"][i][1]), len(seqs[i]))
-                for i in range(len(seqs))]
-        return cls(seqs, recs, bgc_ids, z["bgc_of_seq"].astype(np.int32), type_names,
-                   z["type_of_seq"].astype(np.int32))
+        ali = z["ali"].reshape(-1, 2)
+        meta = ([str(x) for x in z["protein"]], [str(x) for x in z["domain"]], ali[:, 0], ali[:, 1])
+        return cls(None, None, bgc_ids, z["bgc_of_seq"].astype(np.int32), type_names,
+                   z["type_of_seq"].astype(np.int32), blob=z["ascii"], starts=off[:-1],
+                   lengths=np.diff(off).astype(np.int32), meta=meta)
 
 
 @dataclass(frozen=True)
@@ -212,7 +277,8 @@ def _bgc_proteins(bgc, cbp_only: bool):
 
 def extract(source, *, unit: str = "domain", cbp_only: bool = True, alias: Optional[dict] = None,
             domain_types: Optional[Iterable[str]] = None, merge_split_domains: bool = False) -> DomainBatch:
-    """Flatten ``source`` into a DomainBatch.
+    """Flatten ``source`` into a DomainBatch (array form: every protein's sequence once, a domain
+    = a slice of it; see DomainBatch).
 
     source: BGCCollection | BGC | ProteinCollection | iterable of BGC / BGCProtein /
             BGCDomain / str | dict name -> str.
@@ -224,52 +290,87 @@ def extract(source, *, unit: str = "domain", cbp_only: bool = True, alias: Optio
     merge_split_domains: align the domains a protein would have after the reference's
             ``fix_core_split_domains`` post-processing (BGCtoolkit.py:575-687) without running it
             on (and so without modifying) the objects — see ``merged_domain_view``.
+
+    One pass over the objects that only collects numbers and references: per protein its sequence
+    (once), per domain (protein index, ali_from, ali_to, type id, BGC id).  The slice
+    ``protein.sequence[ali_from:ali_to]`` (BGClib/BGClib.py:3240-3241) is then evaluated for all
+    domains at once with Python's slice rules (negative and out-of-range coordinates included) and
+    cut on the device by K1; no per-domain string or record object is made here.
     """
     if unit not in ("domain", "protein"):
         raise ValueError("unit must be 'domain' or 'protein'")
     keep = set(domain_types) if domain_types is not None else None
 
-    seqs: List[str] = []
-    recs: List[DomainRecord] = []
+    parts: List[str] = []          # residue buffer, piecewise: protein sequences / stand-alone strings
+    part_len: List[int] = []
+    part_of = {}                   # id(protein) -> index in parts
+    d_part: List[int] = []         # per domain: which part, raw slice coordinates, ids
+    d_a0: List[int] = []
+    d_a1: List[int] = []
+    d_type: List[str] = []         # type key / BGC name; ids are handed out after empty slices are dropped
+    d_bgc: List[str] = []
+    d_prot: List[str] = []
+    d_dom: List[str] = []
     bgc_ids: List[str] = []
     bgc_index = {}
-    bgc_of: List[int] = []
     type_names: List[str] = []
     type_index = {}
-    type_of: List[int] = []
-    skipped: List[str] = []
 
     def bgc_slot(name: str) -> int:
-        if name not in bgc_index:
-            bgc_index[name] = len(bgc_ids)
+        k = bgc_index.get(name)
+        if k is None:
+            k = bgc_index[name] = len(bgc_ids)
             bgc_ids.append(name)
-        return bgc_index[name]
+        return k
 
     def type_slot(name: str) -> int:
-        if name not in type_index:
-            type_index[name] = len(type_names)
+        k = type_index.get(name)
+        if k is None:
+            k = type_index[name] = len(type_names)
             type_names.append(name)
-        return type_index[name]
+        return k
 
-    def add(seq: str, bgc_name: str, prot_id: str, dom_id: str, tkey: str, a0: int, a1: int):
+    def part_slot(key, seq: str) -> int:
+        k = part_of.get(key)
+        if k is None:
+            k = part_of[key] = len(parts)
+            parts.append(seq)
+            part_len.append(len(seq))
+        return k
+
+    def add(part: int, a0: int, a1: int, bgc: str, prot_id: str, dom_id: str, tkey: str):
         if keep is not None and tkey not in keep:
             return
-        if len(seq) == 0:
-            skipped.append(f"{prot_id}:{dom_id}[{a0}:{a1}] has an empty sequence")
+        d_part.append(part); d_a0.append(a0); d_a1.append(a1)
+        d_type.append(tkey); d_bgc.append(bgc)
+        d_prot.append(prot_id); d_dom.append(dom_id)
+
+    def add_string(s_: str, name: str):
+        if keep is not None and "sequence" not in keep:
             return
-        recs.append(DomainRecord(len(seqs), bgc_name, prot_id, dom_id, tkey, a0, a1, len(seq)))
-        seqs.append(seq)
-        bgc_of.append(bgc_slot(bgc_name))
-        type_of.append(type_slot(tkey))
+        seq = _norm(s_)
+        add(part_slot(("s", len(parts)), seq), 0, len(seq), name, name, "", "sequence")
 
     def add_protein(p, bgc_name: Optional[str]):
         name = bgc_name if bgc_name is not None else (getattr(p, "parent_cluster_id", "") or p.identifier)
+        seq = p.sequence
+        pid = p.identifier
         if unit == "protein":
             tkey = getattr(p, "protein_type", "") or "protein"
-            add(p.sequence, name, p.identifier, "", tkey, 0, len(p.sequence))
+            if keep is None or tkey in keep:
+                add(part_slot(id(p), seq), 0, len(seq), name, pid, "", tkey)
             return
+        part = -1
         for d in (merged_domain_view(p) if merge_split_domains else p.domain_list):
-            add(d.get_sequence(), name, p.identifier, d.ID, type_key(d, alias), d.ali_from, d.ali_to)
+            # type key: external alias, then the domain's own alias, then its ID (type_key())
+            tkey = alias.get(d.ID) if alias else None
+            if tkey is None:
+                tkey = getattr(d, "alias", "") or d.ID
+            if keep is not None and tkey not in keep:
+                continue
+            if part < 0:
+                part = part_slot(id(p), seq)
+            add(part, d.ali_from, d.ali_to, name, pid, d.ID, tkey)
 
     def add_bgc(bgc):
         bgc_slot(bgc.identifier)   # BGCs without eligible domains still get a (zero) row
@@ -285,8 +386,8 @@ def extract(source, *, unit: str = "domain", cbp_only: bool = True, alias: Optio
         for p in source.proteins.values():
             add_protein(p, None)
     elif isinstance(source, dict):
-        for name, s in source.items():
-            add(_norm(s), str(name), str(name), "", "sequence", 0, len(s))
+        for name, s_ in source.items():
+            add_string(s_, str(name))
     else:
         for i, item in enumerate(source):
             if _is_bgc(item):
@@ -296,15 +397,47 @@ def extract(source, *, unit: str = "domain", cbp_only: bool = True, alias: Optio
             elif _is_domain(item):
                 p = item.protein
                 name = getattr(p, "parent_cluster_id", "") or p.identifier
-                add(item.get_sequence(), name, p.identifier, item.ID, type_key(item, alias),
-                    item.ali_from, item.ali_to)
+                tkey = type_key(item, alias)
+                if keep is None or tkey in keep:
+                    add(part_slot(id(p), p.sequence), item.ali_from, item.ali_to, name, p.identifier, item.ID, tkey)
             elif isinstance(item, str):
-                add(_norm(item), f"seq{i}", f"seq{i}", "", "sequence", 0, len(item))
+                add_string(item, f"seq{i}")
             else:
                 raise TypeError(f"cannot extract sequences from {type(item).__name__}")
 
-    return DomainBatch(seqs, recs, bgc_ids, np.asarray(bgc_of, dtype=np.int32), type_names,
-                       np.asarray(type_of, dtype=np.int32), skipped)
+    # ---- all slices at once, with Python's slice rules ------------------------------------------
+    n_all = len(d_part)
+    plen = np.asarray(part_len, dtype=np.int64)
+    pstart = np.zeros(len(parts), dtype=np.int64)
+    if len(parts) > 1:
+        np.cumsum(plen[:-1], out=pstart[1:])
+    part = np.asarray(d_part, dtype=np.int64)
+    L = plen[part] if n_all else np.zeros(0, np.int64)
+    a0 = np.asarray(d_a0, dtype=np.int64)
+    a1 = np.asarray(d_a1, dtype=np.int64)
+    lo = np.clip(np.where(a0 < 0, a0 + L, a0), 0, L)
+    hi = np.clip(np.where(a1 < 0, a1 + L, a1), 0, L)
+    length = np.maximum(hi - lo, 0)
+    ok = length > 0
+    skipped = [f"{d_prot[i]}:{d_dom[i]}[{d_a0[i]}:{d_a1[i]}] has an empty sequence" for i in np.nonzero(~ok)[0].tolist()]
+    sel = np.nonzero(ok)[0]
+    try:
+        raw = "".join(parts).encode("ascii")
+    except UnicodeEncodeError:
+        raise ValueError("sequences must be ASCII protein letters") from None
+    blob = np.frombuffer(raw, dtype=np.uint8) if raw else np.zeros(0, np.uint8)
+    if len(sel) != n_all:
+        sl = sel.tolist()
+        d_prot, d_dom = [d_prot[i] for i in sl], [d_dom[i] for i in sl]
+        d_type, d_bgc = [d_type[i] for i in sl], [d_bgc[i] for i in sl]
+    prot, dom = d_prot, d_dom
+    # ids in order of first appearance among the domains that stay (BGCs of a collection got
+    # their rows above, domains or not)
+    type_ids = np.fromiter((type_slot(t) for t in d_type), dtype=np.int32, count=len(d_type))
+    bgc_of = np.fromiter((bgc_slot(b) for b in d_bgc), dtype=np.int32, count=len(d_bgc))
+    return DomainBatch(None, None, bgc_ids, bgc_of, type_names, type_ids, skipped, blob=blob,
+                       starts=(pstart[part] + lo)[sel], lengths=length[sel].astype(np.int32),
+                       meta=(prot, dom, a0[sel], a1[sel]))
 
 
 def _norm(s: str) -> str:

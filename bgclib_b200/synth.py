@@ -157,3 +157,82 @@ def nrps_pks_100k(n_bgc: int = 4167, seed: int = 20260105) -> SynthCollection:
     """Config 5: ~100k NRPS/PKS domains skewed long (>= 50 % A/C/KS)."""
     return mixed_collection(n_bgc, seed, {"A": 30, "C": 30, "KS420": 15, "AT": 10, "T/ACP": 15},
                             name=f"synthetic {n_bgc} BGCs ~100k NRPS/PKS domains")
+
+
+# ---- the same collections as OBJECTS with the reference's attribute surface ---------------------
+# (BGCCollection.bgcs -> BGC.protein_list / CBPcontent -> BGCProtein.domain_list -> BGCDomain,
+# BGClib/BGClib.py:750-906, 1828-1887, 3222-3241) so that the Python API can be driven end to end
+# at configs[3] scale without the reference installed.
+
+class SynthDomain:
+    __slots__ = ("protein", "ID", "alias", "ali_from", "ali_to")
+
+    def __init__(self, protein, ID, alias, ali_from, ali_to):
+        self.protein, self.ID, self.alias, self.ali_from, self.ali_to = protein, ID, alias, ali_from, ali_to
+
+    def get_sequence(self):                      # BGClib/BGClib.py:3240-3241
+        return self.protein.sequence[self.ali_from:self.ali_to]
+
+
+class SynthProtein:
+    def __init__(self, identifier, sequence, parent_cluster_id):
+        self.identifier, self.parent_cluster_id = identifier, parent_cluster_id
+        self.protein_type, self.role = "", "biosynthetic"
+        self.domain_list = []
+        self._sequence = sequence
+
+    @property
+    def sequence(self):
+        return self._sequence
+
+
+class SynthBGC:
+    def __init__(self, identifier):
+        self.identifier = identifier
+        self.protein_list, self.proteins, self.CBPcontent = [], {}, {}
+
+
+class SynthBGCCollection:
+    def __init__(self):
+        self.bgcs, self.name = {}, ""
+
+
+def as_collection(col: SynthCollection, domains_per_protein: int = 4, seed: int = 1) -> SynthBGCCollection:
+    """``col`` as a collection of BGC / protein / domain objects: the domains of a BGC are laid
+    out, in order, on proteins of ``domains_per_protein`` domains each with short linkers between
+    them.  ``extract(as_collection(col))`` yields col's sequences in col's order."""
+    rng = np.random.default_rng(seed)
+    text = col.ascii.tobytes().decode("ascii")
+    off = col.offsets.tolist()
+    out = SynthBGCCollection()
+    linkers = ["".join(AA20[k] for k in rng.integers(0, 20, size=int(n))) for n in rng.integers(3, 12, size=64)]
+    order = np.argsort(col.bgc_of_seq, kind="stable")
+    assert (order == np.arange(len(col))).all(), "domains of a BGC must be contiguous"
+    bgcs = col.bgc_of_seq.tolist()
+    types = col.type_of_seq.tolist()
+    i, n, lk = 0, len(col), 0
+    while i < n:
+        b = bgcs[i]
+        bgc = SynthBGC(f"BGC{b:06d}")
+        out.bgcs[bgc.identifier] = bgc
+        cds = 0
+        while i < n and bgcs[i] == b:
+            parts, spans, pos = [], [], 0
+            for _ in range(domains_per_protein):
+                if i >= n or bgcs[i] != b:
+                    break
+                link = linkers[lk & 63]
+                lk += 1
+                seq = text[off[i]:off[i + 1]]
+                parts.append(link); parts.append(seq)
+                pos += len(link)
+                spans.append((col.type_names[types[i]], pos, pos + len(seq)))
+                pos += len(seq)
+                i += 1
+            p = SynthProtein(f"{bgc.identifier}~L0+CDS{cds}", "".join(parts), bgc.identifier)
+            p.domain_list = [SynthDomain(p, t, t, a, z) for t, a, z in spans]
+            bgc.protein_list.append(p)
+            bgc.proteins[p.identifier] = p
+            bgc.CBPcontent.setdefault("cbp", []).append(p)
+            cds += 1
+    return out

@@ -100,6 +100,17 @@ int bgca_pack(bgca_engine *e, const uint8_t *ascii, const int64_t *offsets, int3
               const int32_t *type_of_seq, const int32_t *bgc_of_seq, int32_t n_bgc,
               int32_t n_query, int32_t ascii_on_device, void *stream);
 
+/* The same for sequences given as SLICES of a residue buffer: sequence i is
+ * ascii[span_start[i], span_start[i] + span_len[i]).  This is the array form of
+ * BGCDomain.get_sequence() (BGClib/BGClib.py:3240-3241): the buffer holds every protein's
+ * sequence once, a domain is (offset of its protein + ali_from, ali_to - ali_from), and the
+ * slicing happens in K1 on the device instead of 10^5 Python string slices.  Slices may overlap
+ * and leave gaps; each must lie inside the buffer. */
+int bgca_pack_spans(bgca_engine *e, const uint8_t *ascii, int64_t ascii_bytes, const int64_t *span_start,
+                    const int32_t *span_len, int32_t n, const int32_t *type_of_seq,
+                    const int32_t *bgc_of_seq, int32_t n_bgc, int32_t n_query, int32_t ascii_on_device,
+                    void *stream);
+
 /* Persistent database ("a new set of BGCs against a precomputed database",
  * BGClib/Readme.md:18): keeps the batch packed by bgca_pack(..., n_query = 0) resident in HBM
  * as a database and appends n_new query sequences behind it (a later call replaces the previous

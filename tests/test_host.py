@@ -152,6 +152,28 @@ def test_extract_from_collection():
     assert len(extract(col, alias={"ketoacyl-synt": "KS"}, domain_types={"KS"})) == 2
 
 
+def test_synthetic_object_collection_round_trips_through_extract(tmp_path):
+    """synth.as_collection lays a synthetic collection out as BGC / protein / domain objects;
+    extract() must give back exactly its sequences, BGC and type assignment, in order — in span
+    form (each protein's residues once) — and DomainBatch.save/load keep all of it."""
+    from bgclib_b200.extract import DomainBatch
+    col = synth.mibig_scale(30, seed=9)
+    objs = synth.as_collection(col)
+    b = extract(objs)
+    assert b.sequences == col.sequences() and (b.bgc_of_seq == col.bgc_of_seq).all()
+    assert [b.type_names[t] for t in b.type_of_seq] == [col.type_names[t] for t in col.type_of_seq]
+    assert b.sequences == [d.get_sequence() for g in objs.bgcs.values() for p in g.protein_list for d in p.domain_list]
+    blob, starts, lengths = b.spans()
+    assert len(blob) == sum(len(p.sequence) for g in objs.bgcs.values() for p in g.protein_list)
+    assert (lengths == col.lengths).all()
+    b.save(tmp_path / "b.npz")
+    again = DomainBatch.load(tmp_path / "b.npz")
+    assert again.sequences == b.sequences and again.bgc_ids == b.bgc_ids and again.type_names == b.type_names
+    assert [r.protein_identifier for r in again.records] == [r.protein_identifier for r in b.records]
+    sub = b.select_bgcs(b.bgc_ids[3:6][::-1])
+    assert sub.bgc_ids == b.bgc_ids[3:6][::-1] and len(sub) == int(np.isin(b.bgc_of_seq, [3, 4, 5]).sum())
+
+
 def test_extract_protein_units_and_strings(ks_records):
     pc = FakeProteinCollection()
     for r in ks_records:

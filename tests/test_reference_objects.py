@@ -149,3 +149,46 @@ def test_cli_reads_bgccase_pickles_of_the_real_classes(ref, ks_records, tmp_path
     rows = (tmp_path / "x.bgc_similarity.tsv").read_text().splitlines()
     assert rows[0].split("\t")[1:] == list(dbc.bgcs) and [r.split("\t")[0] for r in rows[1:]] == ids
     assert seen["db"].sequences == [r["sequence"] for r in ks_records[8:15]]
+
+
+def test_array_form_extraction_equals_get_sequence_on_real_objects(ref, ks_records):
+    """extract() never calls get_sequence(): it collects (protein, ali_from, ali_to) and evaluates
+    all slices at once.  On the real classes — with coordinates Python's slice rules have to
+    handle (negative, beyond the end, reversed) — the result equals BGCDomain.get_sequence()
+    (BGClib/BGClib.py:3240-3241) domain by domain, and K1's input spans cut exactly those strings."""
+    import numpy as np
+    from bgclib_b200 import extract
+    rng = np.random.default_rng(5)
+    col = ref.BGCCollection()
+    want, want_ids = [], []
+    for k, r in enumerate(ks_records):
+        bgc = ref.BGC()
+        bgc.identifier = f"bgc{k}"
+        col.bgcs[bgc.identifier] = bgc
+        for c in range(2):
+            p = ref.BGCProtein()
+            p.identifier = f"bgc{k}~L0+CDS{c}"
+            p.parent_cluster_id = bgc.identifier
+            p.sequence = r["sequence"][: 100 + 40 * c] if c else r["sequence"]
+            L = len(p.sequence)
+            coords = [(0, L), (5, 60), (-30, L), (L - 10, L + 25), (50, 50), (70, 20), (-L - 5, 12), (L, L + 3)]
+            coords += [tuple(sorted(rng.integers(0, L, 2).tolist())) for _ in range(4)]
+            for a0, a1 in coords:
+                d = ref.BGCDomain(p, "ketoacyl-synt", "PF00109.27", "", "", int(a0), int(a1), 0, 250, 253, 1.0, 1e-9, "")
+                p.domain_list.append(d)
+                if d.get_sequence():
+                    want.append(d.get_sequence())
+                    want_ids.append((bgc.identifier, p.identifier, int(a0), int(a1)))
+            bgc.protein_list.append(p)
+            bgc.proteins[p.identifier] = p
+            bgc.CBPcontent.setdefault("rPKS", []).append(p)
+    b = extract(col)
+    assert b.sequences == want
+    assert [(r.bgc_id, r.protein_identifier, r.ali_from, r.ali_to) for r in b.records] == want_ids
+    assert [r.length for r in b.records] == [len(s) for s in want]
+    blob, starts, lengths = b.spans()
+    text = blob.tobytes().decode()
+    assert [text[a:a + l] for a, l in zip(starts.tolist(), lengths.tolist())] == want
+    assert len(blob) == sum(len(p.sequence) for g in col.bgcs.values() for p in g.protein_list)   # each protein once
+    assert len(b.skipped) == sum(1 for g in col.bgcs.values() for p in g.protein_list for d in p.domain_list
+                                 if not d.get_sequence())
