@@ -38,10 +38,12 @@ for g in (1, 2, 4, 8, 16, 32):
                           [f"-DBGCA_INST_G={g}", f"-DBGCA_INST_MODE={m}", f"-DBGCA_INST_PRESET={pr}"]))
 
 
-for m in (0, 1):                 # multi-pass whole-warp instantiations (queries > 1024 residues)
-    for pr in (0, 1, 2):
-        UNITS.append((f"dp_mp_m{m}_p{pr}.o", "dp_inst.cu",
-                      ["-DBGCA_INST_G=32", "-DBGCA_INST_MP=1", f"-DBGCA_INST_MODE={m}", f"-DBGCA_INST_PRESET={pr}"]))
+for m in (0, 1):                 # multi-pass whole-warp instantiations (queries > 1024 residues), and
+    for pr in (0, 1, 2):         # their 32-bit form (one alignment per word: scores beyond int16)
+        for w32 in (0, 1):
+            UNITS.append((f"dp_mp{'w' if w32 else ''}_m{m}_p{pr}.o", "dp_inst.cu",
+                          ["-DBGCA_INST_G=32", "-DBGCA_INST_MP=1", f"-DBGCA_INST_W32={w32}",
+                           f"-DBGCA_INST_MODE={m}", f"-DBGCA_INST_PRESET={pr}"]))
 
 
 def _sources_mtime() -> float:

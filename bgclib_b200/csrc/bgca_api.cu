@@ -98,6 +98,14 @@ int pick_variant(int Lq, int mode, int n_subjects = 1 << 30)
     return best;   // 0: no packed variant covers Lq
 }
 
+// the 32-bit form of the multi-pass kernel for a query of L residues: fewest passes, rows spread evenly
+int w32_variant(int L)
+{
+    const int npass = (L + BGCA_ONE_PASS_ROWS - 1) / BGCA_ONE_PASS_ROWS;
+    const int K = std::max(17, (L + 32 * npass - 1) / (32 * npass));
+    return BGCA_VARIANT_MP | BGCA_VARIANT_W32 | BGCA_VARIANT_ID(32, K);
+}
+
 // int16 safety of one tile: local scores are bounded by max_sub * min(len),
 // global intermediates by the all-gap path.
 bool fits_int16(int mode, int max_abs_sub, int open, int extend, int Lq, int Ls_max)
@@ -200,7 +208,7 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
         R.info.n_pairs += pr;
         R.info.cells += ce;
         R.info.cells_computed += T.cells;
-        if (T.variant == 0) R.info.n_fallback32++;
+        if (T.variant == 0 || (T.variant & BGCA_VARIANT_W32)) R.info.n_fallback32++;
         R.tiles.push_back(T);
     };
     std::vector<bgca_tile> all;
@@ -220,7 +228,7 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
         T.qa = qa; T.qb = qb; T.s_begin = qa; T.s_end = (qb >= 0 ? qb : qa) + 1;
         T.variant = pick_variant(Lq, mode, 1);
         T.reserved = 1;
-        if (T.variant && !fits_int16(mode, max_abs_sub, open, extend, Lq, Lq)) T.variant = 0;
+        if (T.variant && !fits_int16(mode, max_abs_sub, open, extend, Lq, Lq)) T.variant = 0;   // two pairs: K4
         T.cells = (int64_t)(La + Lb) * (pre[T.s_end] - pre[T.s_begin]);
         produce(T);
     };
@@ -233,11 +241,14 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
         if (counting) { visits += S; return; }
         const int variant = pick_variant(Lq, mode, S);
         const int G = (variant >> 8) & 0xFF;
+        // does any subject of the row take the scores out of int16?  Then its tiles may end up on
+        // the 32-bit form of the multi-pass kernel and are cut for that kernel's 8 groups
+        const bool fits_all = variant && fits_int16(mode, max_abs_sub, open, extend, Lq, max_len_in(sub0, te));
         // subjects per tile: ~spg per alignment group (= subject stream) of the CTA,
         // split evenly over the row and rounded up to a whole number per group
-        const int ngroups = variant ? CTA_THREADS / G : 16;
+        const int ngroups = !variant ? 16 : fits_all ? CTA_THREADS / G : std::min(CTA_THREADS / G, CTA_THREADS / 32);
         int spg_row = spg;
-        if (variant & BGCA_VARIANT_MP)    // bounds the line of parked rows a group keeps between passes
+        if ((variant & BGCA_VARIANT_MP) || !fits_all)   // bounds the line of parked rows a group keeps between passes
             spg_row = std::max(1, std::min(spg, kMpTokensPerGroup / (max_len_in(sub0, te) + 1)));
         const int s_max = ngroups * spg_row;
         const int nchunks = (S + s_max - 1) / s_max;
@@ -245,12 +256,28 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
         chunk = (chunk + ngroups - 1) / ngroups * ngroups;
         for (int s0 = sub0; s0 < te; s0 += chunk) {
             const int s1 = std::min(te, s0 + chunk);
-            bgca_tile T{};
-            T.qa = qa; T.qb = qb; T.s_begin = s0; T.s_end = s1;
-            T.variant = variant;
-            if (variant && !fits_int16(mode, max_abs_sub, open, extend, Lq, max_len_in(s0, s1))) T.variant = 0;
-            T.cells = (int64_t)(La + Lb) * (pre[s1] - pre[s0]);
-            produce(T);
+            if (variant && (fits_all || fits_int16(mode, max_abs_sub, open, extend, Lq, max_len_in(s0, s1)))) {
+                bgca_tile T{};
+                T.qa = qa; T.qb = qb; T.s_begin = s0; T.s_end = s1;
+                T.variant = variant;
+                T.cells = (int64_t)(La + Lb) * (pre[s1] - pre[s0]);
+                produce(T);
+                continue;
+            }
+            // scores beyond int16 (or a query no packed variant covers): one tile per QUERY on the
+            // 32-bit form of the multi-pass kernel; very short queries on the pair-list kernel (K4)
+            for (int h = 0; h < 2; ++h) {
+                const int q = h ? qb : qa;
+                if (q < 0) continue;
+                // square plans: the pair (qb, qa) belongs to qa's tile
+                const int s0q = (h && !cross_only) ? std::max(s0, qb) : s0;
+                if (s0q >= s1) continue;
+                bgca_tile T{};
+                T.qa = q; T.qb = -1; T.s_begin = s0q; T.s_end = s1;
+                T.variant = (len[q] >= BGCA_W32_MIN_ROWS) ? w32_variant(len[q]) : 0;
+                T.cells = (int64_t)len[q] * (pre[s1] - pre[s0q]);
+                produce(T);
+            }
         }
     };
 
@@ -1091,13 +1118,15 @@ try {
             }
         }
         if (multipass) {
-            static const Pair16Launcher mp_table[2][3] = {
-                {launch_pair16_mp_m0_p0, launch_pair16_mp_m0_p1, launch_pair16_mp_m0_p2},
-                {launch_pair16_mp_m1_p0, launch_pair16_mp_m1_p1, launch_pair16_mp_m1_p2}};
+            static const Pair16Launcher mp_table[2][2][3] = {
+                {{launch_pair16_mp_m0_p0, launch_pair16_mp_m0_p1, launch_pair16_mp_m0_p2},
+                 {launch_pair16_mp_m1_p0, launch_pair16_mp_m1_p1, launch_pair16_mp_m1_p2}},
+                {{launch_pair16_mpw_m0_p0, launch_pair16_mpw_m0_p1, launch_pair16_mpw_m0_p2},
+                 {launch_pair16_mpw_m1_p0, launch_pair16_mpw_m1_p1, launch_pair16_mpw_m1_p2}}};
             p.mp_scratch = e->d_mp_scratch.p + mp_lines_used * (size_t)mp_stride;
             p.mp_stride = mp_stride;
             mp_lines_used += (size_t)pair16_mp_max_grid(e->n_sm) * (CTA_THREADS / 32);
-            err = mp_table[local ? 0 : 1][preset](K, p, e->n_sm, ks, &grid);
+            err = mp_table[(variant & BGCA_VARIANT_W32) ? 1 : 0][local ? 0 : 1][preset](K, p, e->n_sm, ks, &grid);
         } else if (gi >= 0) err = table[gi][local ? 0 : 1][preset](K, p, e->n_sm, ks, &grid);
         if (err != cudaSuccess)
             return fail(BGCA_ERR_CUDA, std::string("DP kernel launch (G=") + std::to_string(G) + ",K=" +

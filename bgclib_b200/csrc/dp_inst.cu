@@ -12,18 +12,21 @@
 #ifndef BGCA_INST_MP
 #define BGCA_INST_MP 0
 #endif
+#ifndef BGCA_INST_W32
+#define BGCA_INST_W32 0      // 1 (with BGCA_INST_MP): one alignment per 32-bit word, any score range
+#endif
 
 namespace bgca {
 
 constexpr int kMpMaxCtasPerSm = 2;   // the multi-pass kernels' scratch is sized for this many
 
-template <int G, int K, int MODE, int PRESET, int MP>
+template <int G, int K, int MODE, int PRESET, int MP, int W32 = 0>
 static cudaError_t launch_one(const ScoreParams &p, int n_sm, cudaStream_t st, int *grid_out)
 {
     using Cfg = Pair16Cfg<G, K>;
     constexpr int SMEM = MP ? Cfg::SMEM_BYTES_MP : Cfg::SMEM_BYTES;
     static int ctas_per_sm = 0;   // per instantiation, resolved on first use
-    auto kern = gotoh_pair16_kernel<G, K, MODE, PRESET, MP>;
+    auto kern = gotoh_pair16_kernel<G, K, MODE, PRESET, MP, W32>;
     if (ctas_per_sm == 0) {
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (err != cudaSuccess) return err;
@@ -44,20 +47,25 @@ static cudaError_t launch_one(const ScoreParams &p, int n_sm, cudaStream_t st, i
 #define BGCA_CAT(a, b, c, d, e, f) BGCA_CAT2(a, b, c, d, e, f)
 
 #if BGCA_INST_MP
-cudaError_t BGCA_CAT(launch_pair16_mp, , _m, BGCA_INST_MODE, _p, BGCA_INST_PRESET)(
+#if BGCA_INST_W32
+#define BGCA_MP_NAME launch_pair16_mpw
+#else
+#define BGCA_MP_NAME launch_pair16_mp
+#endif
+cudaError_t BGCA_CAT(BGCA_MP_NAME, , _m, BGCA_INST_MODE, _p, BGCA_INST_PRESET)(
     int K, const ScoreParams &p, int n_sm, cudaStream_t st, int *grid_out)
 {
     switch (K) {
 #define X(G, KK) \
     case KK:     \
-        return launch_one<32, KK, BGCA_INST_MODE, BGCA_INST_PRESET, 1>(p, n_sm, st, grid_out);
+        return launch_one<32, KK, BGCA_INST_MODE, BGCA_INST_PRESET, 1, BGCA_INST_W32>(p, n_sm, st, grid_out);
         BGCA_K_LIST_MP(X, 32)
 #undef X
         default:
             return cudaErrorInvalidValue;
     }
 }
-#if BGCA_INST_MODE == 0 && BGCA_INST_PRESET == 0
+#if BGCA_INST_MODE == 0 && BGCA_INST_PRESET == 0 && !BGCA_INST_W32
 int pair16_mp_max_grid(int n_sm) { return n_sm * kMpMaxCtasPerSm; }
 #endif
 #else

@@ -61,6 +61,38 @@ constexpr uint32_t TOK_IDLE = 25;                  // fills the 64-byte header o
 __device__ __forceinline__ uint32_t pack2(int v) { return ((uint32_t)v & 0xFFFFu) * 0x10001u; }
 __host__ __device__ constexpr uint32_t cpack2(int v) { return ((uint32_t)v & 0xFFFFu) * 0x10001u; }
 
+// The arithmetic of a DP word.  W32 = 0: two alignments per word in s16x2 (the throughput form).
+// W32 = 1: ONE alignment per word in s32 — the same kernel for pairs whose scores can leave int16
+// (whole megasynthase proteins against each other, W-rich sequences, custom matrices); half the
+// cells per instruction, any score range.
+template <int W32> struct DpOps;
+template <> struct DpOps<0> {
+    static constexpr uint32_t NEG = 0x8AD08AD0u;   // NEG16x2
+    static __device__ __forceinline__ uint32_t pack(int v) { return ((uint32_t)v & 0xFFFFu) * 0x10001u; }
+    static __host__ __device__ constexpr uint32_t cpack(int v) { return ((uint32_t)v & 0xFFFFu) * 0x10001u; }
+    static __device__ __forceinline__ uint32_t add(uint32_t a, uint32_t b) { return __vadd2(a, b); }
+    static __device__ __forceinline__ uint32_t sub(uint32_t a, uint32_t b) { return __vsub2(a, b); }
+    static __device__ __forceinline__ uint32_t addmax(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }
+    static __device__ __forceinline__ uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
+    static __device__ __forceinline__ uint32_t max3_relu(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2_relu(a, b, c); }
+    static __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
+    static __device__ __forceinline__ int lo(uint32_t v) { return (int)(int16_t)(v & 0xFFFFu); }
+    static __device__ __forceinline__ int hi(uint32_t v) { return (int)(int16_t)(v >> 16); }
+};
+template <> struct DpOps<1> {
+    static constexpr uint32_t NEG = (uint32_t)(-(1 << 28));
+    static __device__ __forceinline__ uint32_t pack(int v) { return (uint32_t)v; }
+    static __host__ __device__ constexpr uint32_t cpack(int v) { return (uint32_t)v; }
+    static __device__ __forceinline__ uint32_t add(uint32_t a, uint32_t b) { return a + b; }
+    static __device__ __forceinline__ uint32_t sub(uint32_t a, uint32_t b) { return a - b; }
+    static __device__ __forceinline__ uint32_t addmax(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)__viaddmax_s32((int)a, (int)b, (int)c); }
+    static __device__ __forceinline__ uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)__vimax3_s32((int)a, (int)b, (int)c); }
+    static __device__ __forceinline__ uint32_t max3_relu(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)__vimax3_s32_relu((int)a, (int)b, (int)c); }
+    static __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) { return (uint32_t)max((int)a, (int)b); }
+    static __device__ __forceinline__ int lo(uint32_t v) { return (int)v; }
+    static __device__ __forceinline__ int hi(uint32_t) { return 0; }
+};
+
 constexpr int PROF_ROWS = NSYM + 2;   // 24 residues + the two token rows (never scored, must be loadable)
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr)
@@ -121,12 +153,14 @@ template <> struct GapPreset<1> { static constexpr int OPEN = -12, EXT = -1; }; 
 template <> struct GapPreset<2> { static constexpr int OPEN = -11, EXT = -1; };   // BLAST "11/1" read as open+extend
 constexpr int NUM_GAP_PRESETS = 3;
 
-template <int G, int K, int MODE, int PRESET, int MP = 0>
+template <int G, int K, int MODE, int PRESET, int MP = 0, int W32 = 0>
 __global__ void __launch_bounds__(CTA_THREADS, (MP ? 2 : MODE == BGCA_MODE_LOCAL ? Pair16Cfg<G, K>::MIN_CTAS_LOCAL
                                                                               : Pair16Cfg<G, K>::MIN_CTAS_GLOBAL))
 gotoh_pair16_kernel(const ScoreParams p)
 {
     static_assert(!MP || G == 32, "the multi-pass sweep is built for whole-warp groups");
+    static_assert(!W32 || MP, "the 32-bit form is instantiated on the multi-pass kernel only");
+    using Ops = DpOps<W32>;
     using Cfg = Pair16Cfg<G, K>;
     constexpr int CH = Cfg::CH, LPAD = Cfg::LPAD, NGROUPS = Cfg::NGROUPS;
     constexpr bool LOCAL = (MODE == BGCA_MODE_LOCAL);
@@ -151,8 +185,8 @@ gotoh_pair16_kernel(const ScoreParams p)
     for (int i = tid; i < Cfg::BEST_BYTES / 4; i += CTA_THREADS) sbest[i] = 0;
 
     // (e,e) / (o,o): immediates under a preset, pre-packed kernel parameters otherwise
-    const uint32_t ext2 = PRESET ? cpack2(GapPreset<PRESET>::EXT) : p.ext2;
-    const uint32_t open2 = PRESET ? cpack2(GapPreset<PRESET>::OPEN) : p.open2;
+    const uint32_t ext2 = PRESET ? Ops::cpack(GapPreset<PRESET>::EXT) : (W32 ? (uint32_t)p.extend : p.ext2);
+    const uint32_t open2 = PRESET ? Ops::cpack(GapPreset<PRESET>::OPEN) : (W32 ? (uint32_t)p.open : p.open2);
     const uint8_t *const idle_ptr = p.codes;            // header of the packed batch: TOK_IDLE bytes
     int *const my_best = sbest + gid * (Cfg::RING * 2);
     // this lane's 16-byte column of the profile, as a 32-bit shared-window address
@@ -198,7 +232,7 @@ gotoh_pair16_kernel(const ScoreParams p)
                 const int sa = ((ca < NSYM && b < NSYM) ? ssub[ca * NSYM + b] : 0) - p.open;
                 const int sb = ((cb < NSYM && b < NSYM) ? ssub[cb * NSYM + b] : 0) - p.open;
                 const int tt = pos / K, k = pos - tt * K;
-                const uint32_t word = ((uint32_t)sa & 0xFFFFu) | ((uint32_t)sb << 16);
+                const uint32_t word = W32 ? (uint32_t)sa : (((uint32_t)sa & 0xFFFFu) | ((uint32_t)sb << 16));
 #pragma unroll
                 for (int r = 0; r < Cfg::REP; ++r)
                     pw[(((b * CH) + (k >> 2)) * Cfg::W + r * G + tt) * 4 + (k & 3)] = word;
@@ -233,9 +267,9 @@ gotoh_pair16_kernel(const ScoreParams p)
         uint32_t Tn[K], E[K];
         uint32_t best = 0;
         uint32_t h_out = 0, f_out = 0;
-        uint32_t top_h = LOCAL ? open2 : pack2(2 * p.open);     // lane 0: Ho[-1][j]
+        uint32_t top_h = LOCAL ? open2 : Ops::pack(2 * p.open);     // lane 0: Ho[-1][j]
         // column boundary (j = -1) of the row above this lane: Ho[i0-1][-1]
-        const uint32_t hin0 = (LOCAL || gi0 == 0) ? open2 : pack2(2 * p.open + (gi0 - 1) * p.extend);
+        const uint32_t hin0 = (LOCAL || gi0 == 0) ? open2 : Ops::pack(2 * p.open + (gi0 - 1) * p.extend);
         // local mode: the top boundary row is constant (Ho = open, F = 0), so lane 0 takes it with
         // one LOP3 per value instead of a compare and two selects per step
         uint32_t keep_in = (t == 0 && !from_park) ? 0u : 0xFFFFFFFFu;
@@ -254,19 +288,19 @@ gotoh_pair16_kernel(const ScoreParams p)
             // Ho[i0+k][-1], walked down the rows.  The empty asm makes the start value opaque so
             // the K loop-invariant boundary words are rebuilt here (cold path) instead of being
             // hoisted into 2K registers that would stay live across the hot loop.
-            uint32_t col = LOCAL ? open2 : pack2(2 * p.open + gi0 * p.extend);
+            uint32_t col = LOCAL ? open2 : Ops::pack(2 * p.open + gi0 * p.extend);
             asm volatile("" : "+r"(col));
             uint32_t above = hin0;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                Tn[k] = __vadd2(above, P[k]);
+                Tn[k] = Ops::add(above, P[k]);
                 // E advanced to column 0 = max(-inf + ext, Ho[i0+k][-1]); local: any value <= 0 is inert
                 E[k] = LOCAL ? 0u : col;
                 above = col;
-                if (!LOCAL) col = __vadd2(col, ext2);
+                if (!LOCAL) col = Ops::add(col, ext2);
             }
             best = 0;
-            top_h = LOCAL ? open2 : pack2(2 * p.open);
+            top_h = LOCAL ? open2 : Ops::pack(2 * p.open);
         };
 
         int ord = 0;                                            // subjects this lane has finished
@@ -309,7 +343,7 @@ gotoh_pair16_kernel(const ScoreParams p)
                 f_in &= keep_in;
             } else if (t == 0 && !from_park) {  // global: Ho[-1][j] walks down the boundary
                 h_in = top_h;
-                f_in = NEG16x2;
+                f_in = Ops::NEG;
             }
             if (c < TOK_BOUNDARY) {
                 // ================= hot path: one residue of the current subject ========
@@ -324,21 +358,21 @@ gotoh_pair16_kernel(const ScoreParams p)
                     uint32_t up = h_in, F = f_in, h_prev = 0;
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
-                        F = __viaddmax_s16x2(F, ext2, up);
-                        const uint32_t h = LOCAL ? __vimax3_s16x2_relu(Tn[k], E[k], F)
-                                                 : __vimax3_s16x2(Tn[k], E[k], F);
-                        Tn[k] = __vadd2(up, P[k]);              // diagonal term of (k, j+1)
-                        up = __vadd2(h, open2);                 // Ho[k][j]
-                        E[k] = __viaddmax_s16x2(E[k], ext2, up);   // E[k][j+1]
+                        F = Ops::addmax(F, ext2, up);
+                        const uint32_t h = LOCAL ? Ops::max3_relu(Tn[k], E[k], F)
+                                                 : Ops::max3(Tn[k], E[k], F);
+                        Tn[k] = Ops::add(up, P[k]);              // diagonal term of (k, j+1)
+                        up = Ops::add(h, open2);                 // Ho[k][j]
+                        E[k] = Ops::addmax(E[k], ext2, up);   // E[k][j+1]
                         if (LOCAL) {
-                            if (k & 1) best = __vimax3_s16x2(best, h_prev, h);
-                            else if (k == K - 1) best = __vmaxs2(best, h);
+                            if (k & 1) best = Ops::max3(best, h_prev, h);
+                            else if (k == K - 1) best = Ops::max2(best, h);
                         }
                         h_prev = h;
                     }
                     h_out = up;
                     f_out = F;
-                    if (!LOCAL) top_h = __vadd2(top_h, ext2);
+                    if (!LOCAL) top_h = Ops::add(top_h, ext2);
                     if (MP) {                   // bottom row of this pass, by stream position
                         if (park && t == G - 1) __stcg(mp_line + (tau - (G - 1)), make_int2((int)up, (int)F));
                     }
@@ -348,7 +382,7 @@ gotoh_pair16_kernel(const ScoreParams p)
                 const int s = s_first + ord * NGROUPS;
                 if (LOCAL) {
                     int *slot = my_best + (ord & (Cfg::RING - 1)) * 2;
-                    const int lo = (int)(int16_t)(best & 0xFFFFu), hi = (int)(int16_t)(best >> 16);
+                    const int lo = Ops::lo(best), hi = Ops::hi(best);
                     if (G == 1) {               // the lane holds the whole query: nothing to collect
                         emit_pair(p, qa, s, max(lo, 0));
                         emit_pair(p, qb, s, max(hi, 0));
@@ -374,7 +408,7 @@ gotoh_pair16_kernel(const ScoreParams p)
                     // bottom row of the lane left h_out = Ho[K-1].  Picked out here, on the cold path,
                     // so the hot loop carries no capture code.
                     auto final_h = [&](int r) {
-                        uint32_t v = __vsub2(h_out, open2);
+                        uint32_t v = Ops::sub(h_out, open2);
                         // one predicated select per row, as opaque asm: written as a plain
                         // "if (r + 1 == k) v = Tn[k]" chain, ptxas turns Tn[] into an indexed local
                         // array and stores it to the stack in every hot step
@@ -385,8 +419,8 @@ gotoh_pair16_kernel(const ScoreParams p)
                         return v;
                     };
                     const int ra = La - 1 - gi0, rb = Lb - 1 - gi0;   // owned by this lane in this pass?
-                    if (ra >= 0 && ra < K) emit_pair(p, qa, s, (int)(int16_t)(final_h(ra) & 0xFFFFu));
-                    if (rb >= 0 && rb < K) emit_pair(p, qb, s, (int)(int16_t)(final_h(rb) >> 16));
+                    if (ra >= 0 && ra < K) emit_pair(p, qa, s, Ops::lo(final_h(ra)));
+                    if (rb >= 0 && rb < K) emit_pair(p, qb, s, Ops::hi(final_h(rb)));
                 }
                 // idle steps that keep the warp's streams in step (0 unless ALIGN_STREAMS)
                 const int pad = Cfg::ALIGN_STREAMS ? stream_len(ord) - 1 - p.seq_len[s] : 0;

@@ -23,7 +23,8 @@ BGCA_DECL_LAUNCH_GM(32, 0)
 BGCA_DECL_LAUNCH_GM(32, 1)
 // multi-pass (G = 32) instantiations
 #define BGCA_DECL_LAUNCH_MP(M, P) \
-    cudaError_t launch_pair16_mp_m##M##_p##P(int K, const ScoreParams &p, int n_sm, cudaStream_t st, int *grid_out);
+    cudaError_t launch_pair16_mp_m##M##_p##P(int K, const ScoreParams &p, int n_sm, cudaStream_t st, int *grid_out); \
+    cudaError_t launch_pair16_mpw_m##M##_p##P(int K, const ScoreParams &p, int n_sm, cudaStream_t st, int *grid_out);
 BGCA_DECL_LAUNCH_MP(0, 0) BGCA_DECL_LAUNCH_MP(0, 1) BGCA_DECL_LAUNCH_MP(0, 2)
 BGCA_DECL_LAUNCH_MP(1, 0) BGCA_DECL_LAUNCH_MP(1, 1) BGCA_DECL_LAUNCH_MP(1, 2)
 #undef BGCA_DECL_LAUNCH_MP

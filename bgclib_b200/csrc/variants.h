@@ -18,5 +18,7 @@
     BGCA_K_LIST(X, 1) BGCA_K_LIST(X, 2) BGCA_K_LIST(X, 4) BGCA_K_LIST(X, 8) BGCA_K_LIST(X, 16) BGCA_K_LIST(X, 32)
 
 #define BGCA_VARIANT_MP 0x10000   /* flag in bgca_tile.variant: multi-pass instantiation */
+#define BGCA_VARIANT_W32 0x20000  /* with MP: one alignment per 32-bit word (single-query tiles) */
+#define BGCA_W32_MIN_ROWS 272     /* shorter queries leave more than half of a 17-row pass empty */
 #define BGCA_VARIANT_ID(G, K) (((G) << 8) | (K))
 #define BGCA_ONE_PASS_ROWS 1024   /* longest query of a single-pass variant (G = 32, K = 32) */

@@ -49,7 +49,8 @@ typedef struct bgca_engine bgca_engine;
  * (qa, qb) — packed in the two 16-bit halves of every DPX op — against the
  * subjects [s_begin, s_end).  qb == -1 : single query.  variant encodes the
  * kernel instantiation ((G << 8) | K : G lanes per alignment, K query rows per
- * lane), 0 = 32-bit fallback kernel. */
+ * lane; | 0x10000 = multi-pass sweep for queries longer than one pass; | 0x20000 =
+ * its 32-bit form, single query), 0 = 32-bit pair-list kernel. */
 typedef struct bgca_tile {
     int32_t qa, qb, s_begin, s_end;
     int32_t variant;
@@ -67,7 +68,7 @@ typedef struct bgca_plan_info {
     int64_t total_pairs;   /* unique pairs over all ranks                           */
     int64_t total_cells;   /* GCUPS numerator over all ranks                        */
     int32_t n_variants;    /* distinct kernel instantiations used                   */
-    int32_t n_fallback32;  /* tiles routed to the 32-bit kernel                     */
+    int32_t n_fallback32;  /* tiles routed to a 32-bit kernel (scores beyond int16)  */
 } bgca_plan_info;
 
 int bgca_version(void);

@@ -13,7 +13,9 @@ KEEP = [
     "smsp__issue_active.avg.pct_of_peak_sustained_active",
     "smsp__inst_executed.avg.per_cycle_active",
     "sm__inst_executed.sum", "sm__inst_executed_pipe_alu.sum", "sm__inst_executed_pipe_fma.sum",
-    "sm__inst_executed_pipe_lsu.sum",
+    "sm__inst_executed_pipe_lsu.sum", "sm__inst_executed_pipe_fp64.sum",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
     "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",

@@ -97,11 +97,17 @@ def test_planner_balance_and_variants():
             lq = np.maximum(lens[sel["qa"]], np.where(sel["qb"] >= 0, lens[np.maximum(sel["qb"], 0)], 0))
             assert G in (8, 16, 32) and (G * K >= lq).all()
     assert max(loads) / (sum(loads) / 8) < 1.01          # LPT on exact cell counts
-    # sequences beyond the packed kernel's reach (or int16) go to the 32-bit kernel
+    # pairs whose scores can leave int16 go to the 32-bit form of the multi-pass kernel, one query
+    # per tile (0x20000), every pair still planned exactly once
     tiles, info = plan_host(np.array([100, 200, 1500, 3200], np.int32))
-    by_q = {int(t["qa"]): int(t["variant"]) for t in tiles}
-    assert by_q[0] != 0 or info["n_fallback32"] >= 1
-    assert by_q[2] == 0 and info["n_fallback32"] >= 1
+    assert info["total_pairs"] == 10 and info["n_fallback32"] >= 1
+    w32 = [t for t in tiles if int(t["variant"]) & 0x20000]
+    assert w32 and all(int(t["qb"]) == -1 and int(t["variant"]) & 0x10000 for t in w32)
+    # the int16 decision is taken per query PAIR (1500, 3200) and subject chunk: both go, each alone
+    assert {(int(t["qa"]), int(t["s_begin"]), int(t["s_end"])) for t in w32} == {(2, 2, 4), (3, 3, 4)}
+    # short queries with scores beyond int16 stay on the pair-list kernel (variant 0)
+    tiles, info = plan_host(np.array([250, 260], np.int32), max_abs_sub=127, open_gap=-12, extend_gap=-1)
+    assert all(int(t["variant"]) == 0 for t in tiles) and info["n_fallback32"] == info["n_tiles"]
     # global mode: a huge gap-extension penalty leaves int16 -> fallback
     _, info_g = plan_host(np.array([400, 420], np.int32), mode=1, open_gap=-40, extend_gap=-40)
     assert info_g["n_fallback32"] == info_g["n_tiles"]
@@ -111,7 +117,8 @@ def test_planner_balance_and_variants():
     tiles, _ = plan_host(lens4, types4, same_type_only=False, mode=1)
     for t in tiles:
         if t["s_begin"] <= 2 < t["s_end"]:
-            assert t["variant"] == 0, "a 30000-residue subject in global mode must take the 32-bit kernel"
+            assert t["variant"] == 0 or int(t["variant"]) & 0x20000, \
+                "a 30000-residue subject in global mode must take a 32-bit kernel"
     # a persistent database in front of two queries longer than one pass of the packed kernel: the
     # cross tiles take the multi-pass variants and account for every query x database pair
     lens_db = np.array([100, 120, 150, 200, 220, 300, 2500, 2600], np.int32)

@@ -12,7 +12,7 @@ import bgclib_b200
 from bgclib_b200 import synth
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--classes", default="20,30,40,70,120,250,420,600,900,1100,1500,2048,2600")
+ap.add_argument("--classes", default="20,30,40,70,120,250,420,600,900,1100,1500,2048,2600,4000")
 ap.add_argument("--cells", type=float, default=2e12)
 ap.add_argument("--mode", default="local")
 ap.add_argument("--steps", type=int, default=2)
