@@ -566,11 +566,20 @@ def main():
             # `ncu --set full` capture, scaled by launch time to the launches of one step (the DP
             # launches differ only in K; their DRAM bytes per ms are the same within 10 %)
             tr = json.loads((ROOT / "profiles" / "dp_traffic.json").read_text())
-            roofline["traffic"] = tr["dram_bytes_per_launch_ms"] * dp_ms[-1]
-            roofline["traffic_note"] = (f"bytes per step = {tr['dram_bytes_per_launch']} B of the {tr['launch_ms']:.1f} ms "
-                                        f"{tr['kernel']} launch x (step DP ms / launch ms); algorithmic bytes per step = "
-                                        f"{8 * plan['n_pairs'] + int(col.ascii.nbytes)} (two int32 stores per pair + residues); "
-                                        "the scattered 4-byte score stores cost ~8x in 32 B sectors, at 0.03 % of HBM bandwidth")
+            entries = float(n) * float(n)
+            dp_part = tr["dram_bytes_per_launch_ms"] * dp_ms[-1]
+            perm_part = tr["permute_dram_bytes_per_entry"] * entries
+            wb_part = tr["s16_writeback_bytes_per_entry"] * entries
+            alg = 8 * plan["n_pairs"] + int(col.ascii.nbytes)
+            roofline["traffic"] = dp_part + perm_part + wb_part
+            roofline["traffic_over_algorithmic"] = roofline["traffic"] / alg
+            roofline["traffic_note"] = (
+                f"DRAM bytes per step from the committed ncu capture ({tr['source']}): DP launches "
+                f"{tr['dram_bytes_per_launch']} B per {tr['launch_ms']:.1f} ms launch, scaled by DP time = {dp_part:.3g} B; "
+                f"+ the sorted-space int16 staging matrix written back from L2 at most once = {wb_part:.3g} B (upper bound, ncu "
+                f"attributes it to no launch); + permute16_kernel {perm_part:.3g} B (reads the staging matrix, writes the "
+                f"caller's int32 matrix); algorithmic bytes per step = {alg} (two int32 stores per pair + residues); "
+                "round 1 stored scores straight into the caller's index space: 2.73e9 B per step")
         except Exception:
             pass
         if (args.probe or world == 1) and not args.no_probe:

@@ -455,6 +455,7 @@ struct bgca_engine {
     DevBuf<unsigned long long> d_err;
     DevBuf<bgca_tile> d_tiles;
     DevBuf<int2> d_scratch, d_mp_scratch;
+    DevBuf<int16_t> d_s16;                // sorted-space staging of the score matrix (bgca_score)
     DevBuf<uint4> d_scratch_st;
     DevBuf<int32_t> d_scores_host_call;   // bgca_score_all_host's n x n staging matrix
     DevBuf<int32_t> d_st2_items;          // K7 work items (Stats2Item = 4 x int32)
@@ -530,7 +531,7 @@ int bgca_destroy(bgca_engine *e)
     e->d_ascii.release(); e->d_codes.release(); e->d_offsets_orig.release(); e->d_order.release();
     e->d_len.release(); e->d_type.release(); e->d_bgc.release(); e->d_bgc_start.release();
     e->d_bgc_doms.release(); e->d_counters.release(); e->d_pq.release(); e->d_ps.release();
-    e->d_seq_off.release(); e->d_err.release(); e->d_tiles.release(); e->d_scratch.release(); e->d_mp_scratch.release(); e->d_scratch_st.release(); e->d_scores_host_call.release(); e->d_st2_items.release(); e->d_st2_hint.release();
+    e->d_seq_off.release(); e->d_err.release(); e->d_tiles.release(); e->d_scratch.release(); e->d_mp_scratch.release(); e->d_s16.release(); e->d_scratch_st.release(); e->d_scores_host_call.release(); e->d_st2_items.release(); e->d_st2_hint.release();
     e->d_inv_order.release(); e->d_sel_cnt.release(); e->d_sel_cls.release(); e->d_sel_rowstart.release();
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -673,6 +674,8 @@ static int pack_impl(bgca_engine *e, const uint8_t *ascii, int64_t ascii_bytes, 
     CUDA_TRY(cudaMemcpyAsync(e->d_bgc_start.p, e->bgc_start.data(), sizeof(int32_t) * e->bgc_start.size(), cudaMemcpyHostToDevice, st));
     if (!e->bgc_doms.empty())
         CUDA_TRY(cudaMemcpyAsync(e->d_bgc_doms.p, e->bgc_doms.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(e->d_inv_order.reserve(n));
+    CUDA_TRY(cudaMemcpyAsync(e->d_inv_order.p, e->inv_order.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(e->d_err.p, 0xFF, sizeof(unsigned long long), st));
     CUDA_TRY(cudaMemsetAsync(e->d_codes.p, 25, kPackedHeader, st));
     CUDA_TRY(cudaMemsetAsync(e->d_codes.p + off, BGCA_PAD_CODE, 16, st));
@@ -1045,6 +1048,19 @@ try {
         CUDA_TRY(e->d_mp_scratch.reserve(mp_runs * (size_t)pair16_mp_max_grid(e->n_sm) * (CTA_THREADS / 32) *
                                          (size_t)mp_stride));
     }
+    // square plans: the s16x2 kernels stage their scores in sorted space as int16 (coalescing
+    // stores, see ScoreParams::scores16) and one permutation kernel carries them into `scores`
+    const bool stage16 = scores && !e->cross_planned && e->n_db == 0 && e->n <= kPermuteMaxN &&
+                         !std::getenv("BGCA_NO_STAGE16");
+    const int s16_stride = (e->n + 7) & ~7;
+    // does this call write EVERY entry through the s16x2 kernels?  Otherwise the staging matrix
+    // starts out "unwritten" and the permutation leaves such entries of `scores` alone
+    const bool stage_full = e->plan_info.n_pairs == (int64_t)e->n * (e->n + 1) / 2 && e->plan_info.n_fallback32 == 0;
+    if (stage16) {
+        CUDA_TRY(e->d_s16.reserve((size_t)e->n * s16_stride));
+        if (!stage_full)
+            CUDA_TRY(cudaMemsetAsync(e->d_s16.p, BGCA_S16_UNWRITTEN & 0xFF, sizeof(int16_t) * (size_t)e->n * s16_stride, st));
+    }
     CUDA_TRY(e->d_counters.reserve(runs.size() + 1));
     CUDA_TRY(cudaMemsetAsync(e->d_counters.p, 0, sizeof(int32_t) * (runs.size() + 1), st));
     CUDA_TRY(cudaEventRecord(e->ev0, st));
@@ -1053,6 +1069,11 @@ try {
     for (size_t r = 0; r < runs.size(); ++r) {
         const size_t b = runs[r].first, en = runs[r].second;
         const int variant = e->tiles[b].variant;
+        // 32-bit kernels (scores beyond int16) write the caller's matrix directly
+        const bool to_s16 = stage16 && variant != 0 && !(variant & BGCA_VARIANT_W32);
+        p.scores = to_s16 ? nullptr : scores;
+        p.scores16 = to_s16 ? e->d_s16.p : nullptr;
+        p.s16_stride = s16_stride;
         if (variant == 0) {
             // 32-bit fallback: expand the tiles into an explicit (q, s) list
             std::vector<int32_t> pq, ps;
@@ -1139,6 +1160,11 @@ try {
     }
     CUDA_TRY(cudaEventRecord(e->ev1, st));
     e->timed = true;
+    if (stage16) {
+        CUDA_TRY(launch_permute16(e->d_s16.p, s16_stride, e->d_inv_order.p, e->n, scores, stage_full ? 0 : 1,
+                                  e->n_sm, st));
+        e->last_launches++;
+    }
     return BGCA_OK;
 } catch (const std::exception &ex) {   // std::bad_alloc and friends must not cross the C ABI
     return fail(BGCA_ERR_RANGE, std::string("bgca_score: ") + ex.what());

@@ -26,6 +26,13 @@ struct ScoreParams {
     int32_t n_tiles;
     int32_t *tile_counter;     // persistent-CTA work queue head
     int32_t *scores;           // [n*n]      original space, nullable
+    // [n * s16_stride] SORTED space, nullable: where the s16x2 kernels of a square plan leave their
+    // scores (they fit int16 by construction) for permute16_kernel to carry into `scores`.  In
+    // sorted space a tile's row segment is contiguous and the mirrored entries of neighbouring
+    // query pairs share sectors, so L2 merges the stores and each sector reaches DRAM once; written
+    // straight into the caller's index space the same stores cost 6.7x their bytes in DRAM traffic.
+    int16_t *scores16;
+    int32_t s16_stride;
     int32_t *rowbest;          // [n*n_bgc]  original space, nullable
     int32_t *selfsc;           // [n]        original space, nullable
     int32_t n;
@@ -66,6 +73,9 @@ __device__ __forceinline__ void emit_pair(const ScoreParams &p, int q, int s, in
         }
     } else if (s < q) {
         return;
+    } else if (p.scores16) {
+        p.scores16[(size_t)q * p.s16_stride + s] = (int16_t)score;
+        p.scores16[(size_t)s * p.s16_stride + q] = (int16_t)score;
     } else if (p.scores) {
         p.scores[(size_t)oq * p.n + os] = score;
         p.scores[(size_t)os * p.n + oq] = score;

@@ -66,6 +66,12 @@ cudaError_t launch_bgc_reduce(const int32_t *rowbest, const int32_t *selfsc, con
                               const int32_t *bgc_doms, int32_t n_bgc, int64_t *best, int64_t *selfsum,
                               double *sim, cudaStream_t st);
 
+// sorted-space int16 score matrix -> caller's int32 matrix (pack_reduce.cu)
+#define BGCA_S16_UNWRITTEN 0x8080          /* cudaMemset(0x80): below every score the s16x2 kernels can report */
+constexpr int kPermuteMaxN = 100000;       // a sorted row of n int16 has to fit in shared memory
+cudaError_t launch_permute16(const int16_t *S, int stride, const int32_t *inv, int n, int32_t *out,
+                             int skip_unwritten, int n_sm, cudaStream_t st);
+
 int dpx_probe_run(int device, double *out, int n);
 
 }  // namespace bgca

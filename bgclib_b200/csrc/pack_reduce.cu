@@ -1,4 +1,6 @@
 // K1 (packer), K4 launcher, K5 (BGC reduction) — the HBM-bound stages.
+#include <algorithm>
+
 #include "gotoh_s32.cuh"
 #include "launchers.h"
 
@@ -205,6 +207,53 @@ cudaError_t launch_s32(int mode, const ScoreParams &p, const int32_t *pq, const 
     else
         gotoh_s32_kernel<BGCA_MODE_GLOBAL><<<grid, CTA_THREADS, 0, st>>>(p, pq, ps, npairs, scratch,
                                                                         scratch_stride, out_list);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Score matrix, sorted space (int16) -> caller's index space (int32):
+//     out[i][j] = S[inv[i]][inv[j]]       for every entry the s16x2 kernels wrote.
+// A CTA takes output rows one at a time: the sorted row inv[i] (n int16, 16-byte aligned rows)
+// goes to shared memory with 128-bit loads, every thread gathers T[inv[j]] for its columns and
+// the row leaves as coalesced 128-byte lines.  HBM-bound: 2*n*n read + 4*n*n written (+ the
+// inv table, L2-resident).  Entries that still hold the fill value were not computed by these
+// kernels (another rank's tiles, 32-bit tiles, masked type pairs) and are left as the caller
+// initialised them.
+// ---------------------------------------------------------------------------
+constexpr int PERM_THREADS = 512;
+__global__ void __launch_bounds__(PERM_THREADS)
+permute16_kernel(const int16_t *__restrict__ S, int stride, const int32_t *__restrict__ inv, int n,
+                 int32_t *__restrict__ out, int skip_unwritten)
+{
+    extern __shared__ uint4 perm_smem[];
+    int16_t *T = reinterpret_cast<int16_t *>(perm_smem);
+    const int nvec = (n + 7) >> 3;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(S + (size_t)inv[i] * stride);
+        __syncthreads();                    // the previous row has been read out
+        for (int v = threadIdx.x; v < nvec; v += PERM_THREADS) perm_smem[v] = __ldg(src + v);
+        __syncthreads();
+        int32_t *dst = out + (size_t)i * n;
+        for (int j = threadIdx.x; j < n; j += PERM_THREADS) {
+            const int16_t v = T[__ldg(inv + j)];
+            if (!skip_unwritten || v != (int16_t)BGCA_S16_UNWRITTEN) dst[j] = (int32_t)v;
+        }
+    }
+}
+
+cudaError_t launch_permute16(const int16_t *S, int stride, const int32_t *inv, int n, int32_t *out,
+                             int skip_unwritten, int n_sm, cudaStream_t st)
+{
+    const size_t smem = (size_t)((n + 7) >> 3) * 16;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        cudaError_t err = cudaFuncSetAttribute(permute16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        smem_set = smem;
+    }
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(smem, 1)));
+    int grid = std::min(n, n_sm * per_sm);
+    permute16_kernel<<<grid, PERM_THREADS, smem, st>>>(S, stride, inv, n, out, skip_unwritten);
     return cudaGetLastError();
 }
 
