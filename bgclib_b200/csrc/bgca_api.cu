@@ -10,6 +10,7 @@
 #include <numeric>
 #include <queue>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "gotoh_stats2.cuh"
@@ -482,6 +483,18 @@ struct bgca_engine {
     static constexpr int kSideStreams = 4;
     cudaStream_t side[kSideStreams] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[kSideStreams] = {nullptr, nullptr, nullptr, nullptr};
+    // pipelined host call (bgca_score_all_host): finished row blocks of the sorted-space int16
+    // matrix travel to the host on the copy engine while the remaining kernel runs compute
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> ev_pool;     // per-run / per-block events, grown on demand
+    int16_t *h_stage = nullptr;           // pinned copy of the staging matrix (SORTED space, int16)
+    size_t h_stage_elems = 0;
+};
+
+// where bgca_score_all_host wants the matrix: straight into host memory, block by block
+struct HostSink {
+    int32_t *scores_host;
+    bool used = false;                    // set by score_impl when it took the pipelined path
 };
 
 extern "C" {
@@ -518,6 +531,13 @@ try {
         CUDA_TRY(cudaStreamCreateWithFlags(&E->side[i], cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&E->ev_join[i], cudaEventDisableTiming));
     }
+    {
+        // highest priority: the DP kernels are persistent, so a row-block permutation can only start
+        // in the slots a finishing run frees — it has to win them against the next run's CTAs
+        int prio_lo = 0, prio_hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&E->copy_stream, cudaStreamNonBlocking, prio_hi));
+    }
     *out = guard.release();
     return BGCA_OK;
 } catch (const std::exception &ex) {   // std::bad_alloc and friends must not cross the C ABI
@@ -542,6 +562,9 @@ int bgca_destroy(bgca_engine *e)
         if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
         if (e->side[i]) cudaStreamDestroy(e->side[i]);
     }
+    for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->h_stage) cudaFreeHost(e->h_stage);
     delete e;
     return BGCA_OK;
 }
@@ -1004,9 +1027,9 @@ static int run_s32_pairs(bgca_engine *e, ScoreParams &p, const int32_t *d_pq, co
     return BGCA_OK;
 }
 
-int bgca_score(bgca_engine *e, int32_t *scores, int32_t *rowbest, int32_t *selfsc, int32_t type_check,
-               void *stream)
-try {
+static int score_impl(bgca_engine *e, int32_t *scores, int32_t *rowbest, int32_t *selfsc, int32_t type_check,
+                      void *stream, HostSink *sink)
+{
     if (!e || !e->planned) return fail(BGCA_ERR_INVALID, "bgca_score: call bgca_plan first");
     if (rowbest && !e->has_bgc) return fail(BGCA_ERR_INVALID, "bgca_score: rowbest needs bgc_of_seq at pack time");
     if (rowbest && type_check && !e->has_type)
@@ -1061,12 +1084,48 @@ try {
         if (!stage_full)
             CUDA_TRY(cudaMemsetAsync(e->d_s16.p, BGCA_S16_UNWRITTEN & 0xFF, sizeof(int16_t) * (size_t)e->n * s16_stride, st));
     }
+    // Pipelined host sink: with several runs, every entry staged in sorted space and nothing on the
+    // 32-bit kernels, sorted row x is final once every run that holds a tile with qa <= x has
+    // finished.  Runs are then launched in ascending order of their highest query; behind each one
+    // its row block of the int16 staging matrix goes to pinned host memory on the copy engine (no
+    // SM needed: the persistent DP kernels hold them all) and host threads permute its columns,
+    // widen to int32 and put the rows in their place in the caller's matrix — while later runs compute.
+    const bool pipelined = sink && stage16 && stage_full && runs.size() > 1;
+    std::vector<size_t> run_order(runs.size());
+    std::iota(run_order.begin(), run_order.end(), 0);
+    std::vector<int> run_min_q(runs.size(), 0), run_max_q(runs.size(), 0);
+    if (pipelined) {
+        for (size_t r = 0; r < runs.size(); ++r) {
+            int lo = e->n, hi = -1;
+            for (size_t i = runs[r].first; i < runs[r].second; ++i) {
+                const bgca_tile &T = e->tiles[i];
+                lo = std::min(lo, T.qa);
+                hi = std::max(hi, std::max(T.qa, T.qb));
+            }
+            run_min_q[r] = lo; run_max_q[r] = hi;
+        }
+        std::stable_sort(run_order.begin(), run_order.end(), [&](size_t a, size_t b) { return run_max_q[a] < run_max_q[b]; });
+        while (e->ev_pool.size() < 2 * runs.size()) {
+            cudaEvent_t ev;
+            CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            e->ev_pool.push_back(ev);
+        }
+        const size_t elems = (size_t)e->n * s16_stride;
+        if (e->h_stage_elems < elems) {
+            if (e->h_stage) cudaFreeHost(e->h_stage);
+            e->h_stage = nullptr; e->h_stage_elems = 0;
+            CUDA_TRY(cudaHostAlloc(&e->h_stage, elems * sizeof(int16_t), cudaHostAllocDefault));
+            e->h_stage_elems = elems;
+        }
+        sink->used = true;
+    }
     CUDA_TRY(e->d_counters.reserve(runs.size() + 1));
     CUDA_TRY(cudaMemsetAsync(e->d_counters.p, 0, sizeof(int32_t) * (runs.size() + 1), st));
     CUDA_TRY(cudaEventRecord(e->ev0, st));
     CUDA_TRY(cudaEventRecord(e->ev_fork, st));
     int n_side_used = 0;
-    for (size_t r = 0; r < runs.size(); ++r) {
+    for (size_t ri = 0; ri < runs.size(); ++ri) {
+        const size_t r = run_order[ri];
         const size_t b = runs[r].first, en = runs[r].second;
         const int variant = e->tiles[b].variant;
         // 32-bit kernels (scores beyond int16) write the caller's matrix directly
@@ -1131,7 +1190,7 @@ try {
         // variants round-robin over the side streams; the caller's stream joins them below
         cudaStream_t ks = st;
         if (runs.size() > 1) {
-            const int si = (int)(r % bgca_engine::kSideStreams);
+            const int si = (int)(ri % bgca_engine::kSideStreams);
             ks = e->side[si];
             if (si >= n_side_used) {
                 CUDA_TRY(cudaStreamWaitEvent(ks, e->ev_fork, 0));
@@ -1153,6 +1212,59 @@ try {
             return fail(BGCA_ERR_CUDA, std::string("DP kernel launch (G=") + std::to_string(G) + ",K=" +
                                            std::to_string(K) + "): " + cudaGetErrorString(err));
         e->last_launches++;
+        if (pipelined) CUDA_TRY(cudaEventRecord(e->ev_pool[r], ks));
+    }
+    if (pipelined) {
+        // row blocks in launch order: (previous highest query, this run's highest query]
+        int row_lo = 0;
+        std::vector<std::pair<int, int>> blocks;
+        for (size_t ri = 0; ri < runs.size(); ++ri) {
+            const size_t r = run_order[ri];
+            const int row_hi = (ri + 1 == runs.size()) ? e->n : run_max_q[r] + 1;
+            blocks.push_back({row_lo, std::max(row_lo, row_hi)});
+            if (row_hi > row_lo) {
+                for (size_t r2 = 0; r2 < runs.size(); ++r2)       // every run that can still write these rows
+                    if (run_min_q[r2] < row_hi) CUDA_TRY(cudaStreamWaitEvent(e->copy_stream, e->ev_pool[r2], 0));
+                CUDA_TRY(cudaMemcpyAsync(e->h_stage + (size_t)row_lo * s16_stride, e->d_s16.p + (size_t)row_lo * s16_stride,
+                                         sizeof(int16_t) * (size_t)(row_hi - row_lo) * s16_stride, cudaMemcpyDeviceToHost,
+                                         e->copy_stream));
+                row_lo = row_hi;
+            }
+            CUDA_TRY(cudaEventRecord(e->ev_pool[runs.size() + ri], e->copy_stream));
+        }
+        for (int i = 0; i < n_side_used; ++i) {
+            CUDA_TRY(cudaEventRecord(e->ev_join[i], e->side[i]));
+            CUDA_TRY(cudaStreamWaitEvent(st, e->ev_join[i], 0));
+        }
+        CUDA_TRY(cudaEventRecord(e->ev1, st));
+        e->timed = true;
+        // host side: as each block lands in pinned memory, out[order[x]][j] = S[x][inv[j]]
+        const int n = e->n;
+        const int32_t *inv = e->inv_order.data(), *order = e->order.data();
+        const int16_t *hs = e->h_stage;
+        int32_t *out = sink->scores_host;
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const int n_threads = (int)std::min(8u, hw);
+        for (size_t ri = 0; ri < blocks.size(); ++ri) {
+            CUDA_TRY(cudaEventSynchronize(e->ev_pool[runs.size() + ri]));
+            const int x0 = blocks[ri].first, x1 = blocks[ri].second;
+            if (x1 <= x0) continue;
+            auto work = [=](int t) {
+                for (int x = x0 + t; x < x1; x += n_threads) {
+                    const int16_t *src = hs + (size_t)x * s16_stride;
+                    int32_t *dst = out + (size_t)order[x] * n;
+                    for (int j = 0; j < n; ++j) dst[j] = src[inv[j]];
+                }
+            };
+            const int use = std::min(n_threads, x1 - x0);
+            std::vector<std::thread> pool;
+            for (int t = 1; t < use; ++t) pool.emplace_back(work, t);
+            work(0);
+            for (int t = use; t < n_threads; ++t) work(t);      // fewer rows than threads: leftovers stay here
+            for (auto &th : pool) th.join();
+        }
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return BGCA_OK;
     }
     for (int i = 0; i < n_side_used; ++i) {
         CUDA_TRY(cudaEventRecord(e->ev_join[i], e->side[i]));
@@ -1166,6 +1278,12 @@ try {
         e->last_launches++;
     }
     return BGCA_OK;
+}
+
+int bgca_score(bgca_engine *e, int32_t *scores, int32_t *rowbest, int32_t *selfsc, int32_t type_check,
+               void *stream)
+try {
+    return score_impl(e, scores, rowbest, selfsc, type_check, stream, nullptr);
 } catch (const std::exception &ex) {   // std::bad_alloc and friends must not cross the C ABI
     return fail(BGCA_ERR_RANGE, std::string("bgca_score: ") + ex.what());
 }
@@ -1501,11 +1619,11 @@ try {
     const size_t bytes = sizeof(int32_t) * (size_t)n * (size_t)n;
     CUDA_TRY(e->d_scores_host_call.reserve((size_t)n * (size_t)n));
     int32_t *d_scores = e->d_scores_host_call.p;
-    cudaError_t err = cudaMemsetAsync(d_scores, 0, bytes, nullptr);
-    if (err == cudaSuccess) {
-        rc = bgca_score(e, d_scores, nullptr, nullptr, 0, nullptr);
-        if (rc == BGCA_OK) err = cudaMemcpy(scores_host, d_scores, bytes, cudaMemcpyDeviceToHost);
-    }
+    // the pipelined sink needs no cleared matrix (every entry is written); decided inside
+    HostSink sink{scores_host};
+    cudaError_t err = cudaSuccess;
+    rc = score_impl(e, d_scores, nullptr, nullptr, 0, nullptr, std::getenv("BGCA_NO_PIPELINE") ? nullptr : &sink);
+    if (rc == BGCA_OK && !sink.used) err = cudaMemcpy(scores_host, d_scores, bytes, cudaMemcpyDeviceToHost);
     if (rc != BGCA_OK) return rc;
     if (err != cudaSuccess) return fail(BGCA_ERR_CUDA, std::string("bgca_score_all_host: ") + cudaGetErrorString(err));
     return BGCA_OK;

@@ -485,6 +485,34 @@ def test_config3_scale_sample_and_invariants():
     assert res.plan["cells"] == col.pair_stats()["cells"]
 
 
+def test_e2e_host_call_pipelined_blocks(monkeypatch):
+    """bgca_score_all_host with several kernel runs: row blocks are permuted, copied and scattered
+    to the host matrix behind each run while later runs compute.  Mixed lengths (many runs),
+    repeated calls of different sizes on one engine, and the unpipelined path for comparison."""
+    rng = np.random.default_rng(77)
+    eng = get_engine()
+    eng.set_scoring()
+    for n, lo, hi in ((300, 20, 700), (150, 200, 1400), (40, 30, 60), (301, 20, 700)):
+        seqs = [_rand(rng, int(k)) for k in rng.integers(lo, hi, n)]
+        from bgclib_b200.engine import concat_ascii
+        a, off = concat_ascii(seqs)
+        want = oracle.all_pairs(seqs)
+        out = eng.score_all_host(a, off)
+        assert (out == want).all(), (n, lo, hi)
+        monkeypatch.setenv("BGCA_NO_PIPELINE", "1")
+        assert (eng.score_all_host(a, off) == want).all()
+        monkeypatch.delenv("BGCA_NO_PIPELINE")
+    # global mode, and a W-rich sequence that sends tiles to the 32-bit kernels (no pipelining then)
+    eng.set_scoring("BLOSUM62", -12, -1, "global")
+    seqs = [_rand(rng, int(k)) for k in rng.integers(50, 600, 120)]
+    a, off = concat_ascii(seqs)
+    assert (eng.score_all_host(a, off) == oracle.all_pairs(seqs, mode=oracle.MODE_GLOBAL)).all()
+    eng.set_scoring()
+    seqs = [_rand(rng, int(k)) for k in rng.integers(50, 600, 60)] + ["W" * 3000, "WY" * 1500]
+    a, off = concat_ascii(seqs)
+    assert (eng.score_all_host(a, off) == oracle.all_pairs(seqs)).all()
+
+
 def test_e2e_host_call_matches():
     col = synth.ks_like(64, lo=100, hi=180, mean=140, sd=20)
     eng = get_engine()
