@@ -71,13 +71,10 @@ int forced_group_width()
 
 // n_subjects: subjects the query pair meets in its block.  G = 4 / 2 / 1 run 64 / 128 / 256 subject
 // streams per CTA and are only offered when there are enough subjects to keep them busy.
-int pick_variant(int Lq, int mode, int n_subjects = 1 << 30)
+int pick_variant_uncached(int Lq, int force_g, int min_g, int n_subjects)
 {
     int best = 0;
     double best_cost = 0.0;
-    const int force_g = forced_group_width();
-    const int min_g = min_group_width();
-    (void)mode;   // local and global kernels have the same register budget
     if (Lq > BGCA_ONE_PASS_ROWS) {
         // multi-pass whole-warp sweep: the fewest passes of <= 1024 rows, rows spread evenly
         const int npass = (Lq + BGCA_ONE_PASS_ROWS - 1) / BGCA_ONE_PASS_ROWS;
@@ -98,6 +95,28 @@ int pick_variant(int Lq, int mode, int n_subjects = 1 << 30)
     }
     return best;   // 0: no packed variant covers Lq
 }
+
+// One plan asks for the variant of every query pair: the answer depends on the query length and
+// on which of the narrow group widths (G = 4, 2, 1) the number of subjects allows, so a plan
+// keeps a small table instead of scanning the variant list (and the environment) per pair.
+struct VariantPicker {
+    int force_g = forced_group_width(), min_g = min_group_width();
+    std::vector<int> table[4];    // by narrow-width class, then by Lq (<= BGCA_ONE_PASS_ROWS)
+    int operator()(int Lq, int n_subjects)
+    {
+        if (Lq > BGCA_ONE_PASS_ROWS) return pick_variant_uncached(Lq, force_g, min_g, n_subjects);
+        const int cls = (n_subjects >= 4 * CTA_THREADS) ? 3 : (n_subjects >= 2 * CTA_THREADS) ? 2 :
+                        (n_subjects >= CTA_THREADS) ? 1 : 0;
+        std::vector<int> &t = table[cls];
+        if (t.empty()) t.assign(BGCA_ONE_PASS_ROWS + 1, -1);
+        if (t[Lq] < 0) {
+            // the smallest subject count of the class stands for all of it (thresholds are 4 * 256 / G)
+            static const int rep[4] = {1, CTA_THREADS, 2 * CTA_THREADS, 4 * CTA_THREADS};
+            t[Lq] = pick_variant_uncached(Lq, force_g, min_g, rep[cls]);
+        }
+        return t[Lq];
+    }
+};
 
 // the 32-bit form of the multi-pass kernel for a query of L residues: fewest passes, rows spread evenly
 int w32_variant(int L)
@@ -149,6 +168,8 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
                      int open, int extend, int rank, int world)
 {
     PlanResult R;
+    VariantPicker pick_variant;
+    (void)mode;   // local and global kernels have the same register budget
     std::vector<int64_t> pre(n + 1, 0);
     for (int i = 0; i < n; ++i) pre[i + 1] = pre[i] + len[i];
     // The packer sorts by (type, role, length): lengths are non-decreasing only inside one run.
@@ -227,7 +248,7 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
         const int Lq = std::max(La, Lb);
         bgca_tile T{};
         T.qa = qa; T.qb = qb; T.s_begin = qa; T.s_end = (qb >= 0 ? qb : qa) + 1;
-        T.variant = pick_variant(Lq, mode, 1);
+        T.variant = pick_variant(Lq, 1);
         T.reserved = 1;
         if (T.variant && !fits_int16(mode, max_abs_sub, open, extend, Lq, Lq)) T.variant = 0;   // two pairs: K4
         T.cells = (int64_t)(La + Lb) * (pre[T.s_end] - pre[T.s_begin]);
@@ -240,7 +261,7 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
         const int S = te - sub0;
         if (S <= 0) return;
         if (counting) { visits += S; return; }
-        const int variant = pick_variant(Lq, mode, S);
+        const int variant = pick_variant(Lq, S);
         const int G = (variant >> 8) & 0xFF;
         // does any subject of the row take the scores out of int16?  Then its tiles may end up on
         // the 32-bit form of the multi-pass kernel and are cut for that kernel's 8 groups
@@ -1090,7 +1111,22 @@ static int score_impl(bgca_engine *e, int32_t *scores, int32_t *rowbest, int32_t
     // its row block of the int16 staging matrix goes to pinned host memory on the copy engine (no
     // SM needed: the persistent DP kernels hold them all) and host threads permute its columns,
     // widen to int32 and put the rows in their place in the caller's matrix — while later runs compute.
-    const bool pipelined = sink && stage16 && stage_full && runs.size() > 1;
+    bool pipelined = sink && stage16 && stage_full && runs.size() > 1;
+    if (pipelined) {
+        // pinned copy of the staging matrix; a host that cannot pin that much takes the plain path
+        const size_t elems = (size_t)e->n * s16_stride;
+        if (e->h_stage_elems < elems) {
+            if (e->h_stage) cudaFreeHost(e->h_stage);
+            e->h_stage = nullptr; e->h_stage_elems = 0;
+            if (cudaHostAlloc(&e->h_stage, elems * sizeof(int16_t), cudaHostAllocDefault) == cudaSuccess)
+                e->h_stage_elems = elems;
+            else {
+                (void)cudaGetLastError();
+                e->h_stage = nullptr;
+                pipelined = false;
+            }
+        }
+    }
     std::vector<size_t> run_order(runs.size());
     std::iota(run_order.begin(), run_order.end(), 0);
     std::vector<int> run_min_q(runs.size(), 0), run_max_q(runs.size(), 0);
@@ -1109,13 +1145,6 @@ static int score_impl(bgca_engine *e, int32_t *scores, int32_t *rowbest, int32_t
             cudaEvent_t ev;
             CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
             e->ev_pool.push_back(ev);
-        }
-        const size_t elems = (size_t)e->n * s16_stride;
-        if (e->h_stage_elems < elems) {
-            if (e->h_stage) cudaFreeHost(e->h_stage);
-            e->h_stage = nullptr; e->h_stage_elems = 0;
-            CUDA_TRY(cudaHostAlloc(&e->h_stage, elems * sizeof(int16_t), cudaHostAllocDefault));
-            e->h_stage_elems = elems;
         }
         sink->used = true;
     }
