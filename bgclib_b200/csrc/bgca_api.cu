@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <exception>
+#include <map>
 #include <memory>
 #include <numeric>
 #include <queue>
@@ -240,8 +241,10 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
     };
     if (!small_plan) R.tiles.reserve(((size_t)n * ((size_t)n / (2 * 128 * (size_t)spg) + 2) / 2) / (size_t)world + 64);
 
-    bool counting = false;          // pre-pass of cross plans: only add up the subjects visited
+    bool counting = false;          // pre-pass: only add up the subjects visited (in all, and per variant)
     int64_t visits = 0;
+    std::map<int, int64_t> visits_of_variant;
+    std::map<int, int> spg_of_variant;     // multi-rank plans: shorter tiles for runs with few of them
     auto self_tile = [&](int qa, int qb) {
         if (counting) return;
         const int La = len[qa], Lb = (qb >= 0) ? len[qb] : 0;
@@ -260,8 +263,8 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
         const int Lq = std::max(La, Lb);
         const int S = te - sub0;
         if (S <= 0) return;
-        if (counting) { visits += S; return; }
         const int variant = pick_variant(Lq, S);
+        if (counting) { visits += S; visits_of_variant[variant] += S; return; }
         const int G = (variant >> 8) & 0xFF;
         // does any subject of the row take the scores out of int16?  Then its tiles may end up on
         // the 32-bit form of the multi-pass kernel and are cut for that kernel's 8 groups
@@ -270,8 +273,12 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
         // split evenly over the row and rounded up to a whole number per group
         const int ngroups = !variant ? 16 : fits_all ? CTA_THREADS / G : std::min(CTA_THREADS / G, CTA_THREADS / 32);
         int spg_row = spg;
+        {
+            auto it = spg_of_variant.find(variant);
+            if (it != spg_of_variant.end()) spg_row = it->second;
+        }
         if ((variant & BGCA_VARIANT_MP) || !fits_all)   // bounds the line of parked rows a group keeps between passes
-            spg_row = std::max(1, std::min(spg, kMpTokensPerGroup / (max_len_in(sub0, te) + 1)));
+            spg_row = std::max(1, std::min(spg_row, kMpTokensPerGroup / (max_len_in(sub0, te) + 1)));
         const int s_max = ngroups * spg_row;
         const int nchunks = (S + s_max - 1) / s_max;
         int chunk = (S + nchunks - 1) / nchunks;
@@ -371,6 +378,20 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
         counting = false;
         const int64_t target_tiles = 16LL * 2 * 148 * world;
         spg = (int)std::max<int64_t>(2, std::min<int64_t>(spg, visits / (target_tiles * 16)));
+    } else if (world > 1) {
+        // Large plan shared by several ranks: a kernel run (one variant) that leaves a rank fewer
+        // than ~8 tiles per CTA slot ends in a tail of half-idle SMs — with many variants (mixed
+        // domain lengths) that was 1.3 % of the step at 8 GPUs.  Such runs get shorter tiles.
+        counting = true;
+        generate();
+        counting = false;
+        const int64_t want_tiles = 8LL * 2 * 148 * world;
+        for (const auto &kv : visits_of_variant) {
+            const int G = (kv.first >> 8) & 0xFF;
+            const int ngroups = kv.first ? CTA_THREADS / std::max(G, 1) : 16;
+            const int64_t s = kv.second / (want_tiles * ngroups);
+            if (s < spg) spg_of_variant[kv.first] = (int)std::max<int64_t>(4, s);
+        }
     }
     generate();
 

@@ -132,6 +132,29 @@ def test_planner_balance_and_variants():
     assert info["n_fallback32"] == info["n_tiles"] and info["total_pairs"] == 2 * 6 + 2
 
 
+def test_multi_rank_large_plan_cuts_shorter_tiles_and_still_covers_everything():
+    """Large plans shared by several ranks cut shorter tiles for kernel runs that would leave a
+    rank only a few tiles per CTA slot; the shares still partition the pairs and cells exactly."""
+    col = synth.mibig_scale(250, seed=11)                 # ~6 000 mixed domains, 6 types: a "large" plan
+    order = np.lexsort((col.lengths, col.type_of_seq))
+    L, T = col.lengths[order].astype(np.int32), col.type_of_seq[order].astype(np.int32)
+    one, info1 = plan_host(L, T, same_type_only=True)
+    pairs = cells = 0
+    n_tiles = 0
+    seen = np.zeros(len(L), dtype=np.int64)               # subjects visited per query row, summed over ranks
+    for r in range(8):
+        tiles, info = plan_host(L, T, same_type_only=True, rank=r, world=8)
+        pairs += info["n_pairs"]; cells += info["cells"]; n_tiles += info["n_tiles"]
+        assert info["total_pairs"] == info1["total_pairs"] and info["total_cells"] == info1["total_cells"]
+        np.add.at(seen, tiles["qa"], tiles["s_end"] - tiles["s_begin"])
+    assert pairs == info1["total_pairs"] == col.pair_stats(same_type_only=True)["pairs"]
+    assert cells == info1["total_cells"] == col.pair_stats(same_type_only=True)["cells"]
+    assert n_tiles > info1["n_tiles"]                     # shorter tiles than the single-rank plan
+    seen1 = np.zeros(len(L), dtype=np.int64)
+    np.add.at(seen1, one["qa"], one["s_end"] - one["s_begin"])
+    assert (seen == seen1).all()                          # every query row meets the same subjects
+
+
 def test_extract_from_collection():
     p1 = "M" + "ACDEFGHIKL" * 6
     p2 = "MNPQRSTVWY" * 5
