@@ -565,6 +565,10 @@ def main():
             # dram__bytes_read.sum + dram__bytes_write.sum of one DP launch from the committed
             # `ncu --set full` capture, scaled by launch time to the launches of one step (the DP
             # launches differ only in K; their DRAM bytes per ms are the same within 10 %)
+            if world > 1:
+                # the committed capture is a 1-GPU step; under N ranks every rank fills, reads and permutes
+                # the whole staging matrix for 1/N of the pairs, which this scaling does not describe
+                raise LookupError("traffic is reported for the 1-GPU step only")
             tr = json.loads((ROOT / "profiles" / "dp_traffic.json").read_text())
             entries = float(n) * float(n)
             dp_part = tr["dram_bytes_per_launch_ms"] * dp_ms[-1]
