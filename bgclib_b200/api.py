@@ -24,7 +24,7 @@ from typing import List, Optional
 import numpy as np
 
 from .engine import ALNSTAT_DTYPE, Engine, MODE_LOCAL, resolve_mode
-from .extract import DomainBatch, DomainRecord, extract
+from .extract import DomainBatch, DomainRecord, RecordView, extract
 
 _ENGINES = {}
 
@@ -52,7 +52,8 @@ def _dist():
 class DomainPairScores:
     scores: np.ndarray              # int32 [n, n], symmetric, diagonal = self scores
                                     # (query-vs-database: [n_query, n_db])
-    index: List[DomainRecord]       # row identity (and column identity when database is None)
+    index: List[DomainRecord]       # row identity (and column identity when database is None); a lazy
+                                    # sequence (RecordView): the records are built when first looked at
     computed: Optional[np.ndarray]  # bool, same shape, when same_type_only masked some pairs, else None
     plan: dict                      # tile-plan statistics of this rank
     db_index: Optional[List[DomainRecord]] = None   # column identity of a query-vs-database run
@@ -187,10 +188,10 @@ def domain_pair_scores(source, *, database=None, mode="local", matrix="BLOSUM62"
         computed = scores != INT32_MIN
         if resolve_mode(mode) == MODE_LOCAL:
             scores = torch.where(computed, scores, torch.zeros_like(scores))
-    db_index = None if db is None else db.records
+    db_index = None if db is None else db.record_view()
     if return_device:
-        return DomainPairScores(scores, batch.records, computed, plan, db_index, rows)
-    return DomainPairScores(scores.cpu().numpy(), batch.records,
+        return DomainPairScores(scores, batch.record_view(), computed, plan, db_index, rows)
+    return DomainPairScores(scores.cpu().numpy(), batch.record_view(),
                             None if computed is None else computed.cpu().numpy(), plan, db_index, rows)
 
 
@@ -278,9 +279,9 @@ def bgc_similarity(source, *, database=None, matrix="BLOSUM62", open_gap_score=-
         dist.all_reduce(selfsc, op=dist.ReduceOp.MAX)
     sim, best, selfsum = eng.reduce_bgc(rowbest, selfsc)
     if return_device:
-        return BGCSimilarity(sim, best, selfsum, ids, batch.records, plan)
+        return BGCSimilarity(sim, best, selfsum, ids, batch.record_view(), plan)
     return BGCSimilarity(sim.cpu().numpy(), best.cpu().numpy(), selfsum.cpu().numpy(), ids,
-                         batch.records, plan)
+                         batch.record_view(), plan)
 
 
 _PLAN_SUMS = ("n_tiles", "n_pairs", "cells", "cells_computed", "n_fallback32")
@@ -350,7 +351,7 @@ def _bgc_similarity_cross(q: DomainBatch, d: DomainBatch, matrix, open_gap_score
     best_dq = best[Bq:, :Bq].contiguous()
     if not return_device:
         sim_x, best_qd, best_dq, selfsum = (x.cpu().numpy() for x in (sim_x, best_qd, best_dq, selfsum))
-    return BGCSimilarity(sim_x, best_qd, selfsum[:Bq], list(q.bgc_ids), q.records + d.records, plan,
+    return BGCSimilarity(sim_x, best_qd, selfsum[:Bq], list(q.bgc_ids), RecordView(q, d), plan,
                          list(d.bgc_ids), selfsum[Bq:], best_dq)
 
 
@@ -419,7 +420,7 @@ def _bgc_similarity_persistent(q: DomainBatch, db: PackedDatabase, same_type_onl
     best_dq = best[:Bd, Bd:].contiguous()
     if not return_device:
         sim_x, best_qd, best_dq, selfsum = (x.cpu().numpy() for x in (sim_x, best_qd, best_dq, selfsum))
-    return BGCSimilarity(sim_x, best_qd, selfsum[Bd:], list(q.bgc_ids), q.records + d.records, plan,
+    return BGCSimilarity(sim_x, best_qd, selfsum[Bd:], list(q.bgc_ids), RecordView(q, d), plan,
                          list(d.bgc_ids), selfsum[:Bd], best_dq)
 
 
@@ -472,7 +473,7 @@ def domain_pair_stats(source, pairs=None, *, mode="local", matrix="BLOSUM62", op
             eng = get_engine(device)
             pairs_t, out = eng.pair_stats_above(t.contiguous(), int(min_score), same_type_only)
             stats = np.ascontiguousarray(out.cpu().numpy()).view(ALNSTAT_DTYPE).reshape(-1)
-            return DomainPairStats(stats, pairs_t.cpu().numpy(), batch.records)
+            return DomainPairStats(stats, pairs_t.cpu().numpy(), batch.record_view())
         keep = t >= int(min_score)
         if sc.computed is not None:
             keep &= sc.computed
@@ -500,7 +501,7 @@ def domain_pair_stats(source, pairs=None, *, mode="local", matrix="BLOSUM62", op
                 pairs[mine, 0].copy(), pairs[mine, 1].copy(), None if known is None else known[mine].copy())
         dist.all_reduce(out, op=dist.ReduceOp.SUM)
     stats = np.ascontiguousarray(out.cpu().numpy()).view(ALNSTAT_DTYPE).reshape(-1)
-    return DomainPairStats(stats, pairs, batch.records)
+    return DomainPairStats(stats, pairs, batch.record_view())
 
 
 def attach(collection_cls=None):

@@ -36,6 +36,39 @@ class DomainRecord:
     length: int
 
 
+class RecordView:
+    """``DomainBatch.records`` of one or more batches as a read-only sequence that is only built
+    when somebody looks at it: result objects carry the row identity of 10^5 domains without
+    paying for 10^5 DomainRecord objects on every call (150 ms at 60 601 domains)."""
+
+    def __init__(self, *batches):
+        self._batches = batches
+        self._list = None
+
+    def _get(self):
+        if self._list is None:
+            out = []
+            for b in self._batches:
+                out.extend(b.records)
+            self._list = out
+        return self._list
+
+    def __len__(self):
+        return sum(len(b) for b in self._batches)
+
+    def __iter__(self):
+        return iter(self._get())
+
+    def __getitem__(self, k):
+        return self._get()[k]
+
+    def __eq__(self, other):
+        return list(self) == list(other)
+
+    def __repr__(self):
+        return f"RecordView({len(self)} domains)"
+
+
 class DomainBatch:
     """The flattened collection the engine packs.  Two interchangeable forms:
 
@@ -91,6 +124,10 @@ class DomainBatch:
             self._blob = np.frombuffer(raw, dtype=np.uint8) if raw else np.zeros(0, np.uint8)
             self._starts, self._lengths = starts, lens.astype(np.int32)
         return self._blob, self._starts, self._lengths
+
+    def record_view(self) -> "RecordView":
+        """``records`` without building them until they are looked at."""
+        return RecordView(self)
 
     @property
     def records(self) -> List["DomainRecord"]:
