@@ -26,6 +26,9 @@ Outputs (next to --out, TSV like write_metadata's tables, BGCtoolkit.py:1045-113
   <out>.bgc_distance.tsv     1 - similarity (the "distance calculation" of BGClib/Readme.md:16-18)
   <out>.bgc_best.tsv         the integer numerators best[a,b]
   <out>.domain_scores.npy + <out>.domain_index.tsv    (with --domain-scores)
+  <out>.domain_stats.tsv     (with --domain-stats MIN_SCORE) one line per domain pair whose score reaches
+                             MIN_SCORE: identities, alignment columns, coordinates, gaps — the input an
+                             identity-based distance needs (selected and computed on the device)
 """
 from __future__ import annotations
 
@@ -180,6 +183,9 @@ def main(argv=None):
     ap.add_argument("--all-types", action="store_true", help="compare domains of different types too")
     ap.add_argument("--all-proteins", action="store_true", help="--bgccase: not only core biosynthetic proteins")
     ap.add_argument("--domain-scores", action="store_true", help="also write the domain x domain score matrix")
+    ap.add_argument("--domain-stats", type=int, default=None, metavar="MIN_SCORE",
+                    help="also write alignment statistics (identities, columns, coordinates) of every domain "
+                         "pair whose score reaches MIN_SCORE (not with a database)")
     args = ap.parse_args(argv)
     if bool(args.fasta) == bool(args.bgccase):
         ap.error("give exactly one of --fasta / --bgccase")
@@ -212,6 +218,21 @@ def main(argv=None):
                 f.write(f"row\t{r.index}\t{r.bgc_id}\t{r.protein_identifier}\t{r.type_key}\t{r.length}\n")
             for r in (dps.db_index or []):
                 f.write(f"col\t{r.index}\t{r.bgc_id}\t{r.protein_identifier}\t{r.type_key}\t{r.length}\n")
+    if args.domain_stats is not None:
+        if db is not None:
+            ap.error("--domain-stats compares the input with itself; drop the --db-* option")
+        st = api.domain_pair_stats(batch, min_score=args.domain_stats, mode=args.mode,
+                                   same_type_only=not args.all_types, **gap)
+        recs = st.index
+        with open(f"{out}.domain_stats.tsv", "w") as f:
+            f.write("domain_a\tdomain_b\tBGC_a\tBGC_b\ttype\t" + "\t".join(st.stats.dtype.names) + "\tidentity\n")
+            ident = st.identity
+            for k, (i, j) in enumerate(st.pairs.tolist()):
+                a, b = recs[i], recs[j]
+                f.write(f"{a.protein_identifier}:{a.ali_from}-{a.ali_to}\t{b.protein_identifier}:{b.ali_from}-{b.ali_to}\t"
+                        f"{a.bgc_id}\t{b.bgc_id}\t{a.type_key}\t"
+                        + "\t".join(str(int(st.stats[name][k])) for name in st.stats.dtype.names)
+                        + f"\t{ident[k]:.6f}\n")
     print(f"{len(batch)} domains in {len(res.bgc_ids)} BGCs"
           + (f" vs {len(db)} domains in {len(res.db_bgc_ids)} BGCs" if db is not None else "")
           + f": {res.plan.get('total_pairs', 0)} domain pairs aligned -> {out}.bgc_similarity.tsv")

@@ -613,6 +613,18 @@ def test_cli_end_to_end(tmp_path, ks_records, af293):
     assert (dmat == 1.0 - want).all() and (np.diag(dmat) == 0).all()
     # query-vs-database through the CLI
     assert cli.main(["--fasta", str(fa), "--db-fasta", str(fa), "--out", str(tmp_path / "x")]) == 0
+    # alignment statistics of the pairs above a score, selected on the device
+    assert cli.main(["--fasta", str(fa), "--out", str(tmp_path / "s"), "--domain-stats", "400"]) == 0
+    lines = (tmp_path / "s.domain_stats.tsv").read_text().splitlines()
+    sc = oracle.all_pairs(seqs)
+    want_pairs = np.argwhere(np.triu(sc >= 400, k=1))
+    want = oracle.stats_list(seqs, want_pairs[:, 0], want_pairs[:, 1])
+    assert len(lines) == 1 + len(want_pairs) > 1
+    cols = lines[0].split("\t")
+    for line, w in zip(lines[1:], want):
+        row = dict(zip(cols, line.split("\t")))
+        assert all(int(row[k]) == int(w[k]) for k in want.dtype.names)
+        assert abs(float(row["identity"]) - int(w["identities"]) / int(w["columns"])) < 1e-6
 
 
 def test_cli_bgccase_bgclist_comparative(tmp_path, af293, ks_records, monkeypatch):
