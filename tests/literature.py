@@ -36,6 +36,11 @@ SW1981 = _matrix({}, default=-1, diagonal=3)
 # PairwiseAligner = match 1, mismatch 0, every gap score 0.
 IDENTITY = _matrix({}, default=0, diagonal=1)
 
+# Biopython, Bio/pairwise2.py module docstring: globalms("ACCGT", "ACG", 2, -1, -.5, -.1) — match 2,
+# mismatch -1, gap open -0.5, extend -0.1, end gaps penalised — prints "Score=5" (ACCGT / A-CG-).
+# Everything times 10 to stay integer.
+PAIRWISE2_MS = _matrix({}, default=-10, diagonal=20)
+
 CASES = [
     ("durbin-global", "HEAGAWGHEE", "PAWHEAE", "global", DURBIN_BLOSUM50, -8, -8, 1,
      "Durbin et al. 1998, Fig. 2.5: bottom-right cell of the global DP matrix, linear gap d = 8"),
@@ -49,6 +54,8 @@ CASES = [
      "Biopython Tutorial, local mode: aligner.score('AGAACTC', 'GAACT') == 5.0"),
     ("biopython-tutorial-blosum62", "KEVLA", "EVL", "global", "BLOSUM62", 0, 0, 13,
      "Biopython Tutorial, substitution matrices: BLOSUM62, 'KEVLA' vs 'EVL' scores 13.0"),
+    ("biopython-pairwise2-doc", "ACCGT", "ACG", "global", PAIRWISE2_MS, -5, -1, 50,
+     "Bio.pairwise2 docstring: globalms('ACCGT', 'ACG', 2, -1, -.5, -.1) -> Score=5 (x10), end gaps penalised"),
 ]
 
 # the 1981 paper also prints the alignment itself: GCCAUUG (query 3..10) over GCC-UCG (subject 2..8)
