@@ -196,7 +196,7 @@ gotoh_stats2_kernel(const Stats2Params p)
                 }
             }
             best = EMPTY; bend = 0xFFFFFFFFu;
-            if (HINT) thr = (p.hint[pair] + ST2_BIAS) * 1024;
+            if (HINT) thr = (min(max(p.hint[pair], 0), 1 << 20) + ST2_BIAS) * 1024;   // any caller value stays in range
             j = 0;
             Ls_cur = p.seq_len[s];
             top_ho = (uint32_t)((2 * p.open + ST2_BIAS) * 1024);
@@ -334,7 +334,7 @@ gotoh_stats2_kernel(const Stats2Params p)
                     bgca_alnstats r;
                     r.score = (int)(rh >> 10) - ST2_BIAS;
                     if (HINT) {                 // no cell reached the hinted score: the hint was too high
-                        if (r.score < p.hint[pair]) atomicAdd(p.redo_count, 1);
+                        if (r.score < min(max(p.hint[pair], 0), 1 << 20)) atomicAdd(p.redo_count, 1);
                     }
                     r.identities = (int)(rh & 1023u);
                     if (LOCAL) {
