@@ -432,38 +432,66 @@ template <typename T>
 struct DevBuf {
     T *p = nullptr;
     size_t cap = 0;
-    cudaError_t reserve(size_t count)
+    void *base = nullptr;       // what cudaMalloc returned (p may sit further in: see alloc)
+    // window4g: the buffer must not cross a 4 GiB address boundary — the DP kernels advance their
+    // token pointer with a 32-bit add on its low half (gotoh_pair16.cuh, advance_lo32).  An
+    // allocation that crosses one is made again at twice the size and used from the boundary on.
+    static cudaError_t alloc(size_t bytes, bool window4g, void **base_out, T **p_out)
+    {
+        void *raw = nullptr;
+        bytes = std::max<size_t>(bytes, 1);
+        cudaError_t e = cudaMalloc(&raw, bytes);
+        if (e != cudaSuccess) return e;
+        auto crosses = [&](const void *q) {
+            const uintptr_t a = (uintptr_t)q;
+            return (a >> 32) != ((a + bytes - 1) >> 32);
+        };
+        T *use = static_cast<T *>(raw);
+        if (window4g && crosses(raw)) {
+            if (bytes > ((size_t)1 << 32)) { cudaFree(raw); return cudaErrorInvalidValue; }
+            cudaFree(raw);
+            e = cudaMalloc(&raw, 2 * bytes);
+            if (e != cudaSuccess) return e;
+            use = static_cast<T *>(raw);
+            if (crosses(raw)) use = reinterpret_cast<T *>((((uintptr_t)raw >> 32) + 1) << 32);
+        }
+        *base_out = raw;
+        *p_out = use;
+        return cudaSuccess;
+    }
+    cudaError_t reserve(size_t count, bool window4g = false)
     {
         if (count <= cap && p) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+        release();
+        cudaError_t e = alloc(count * sizeof(T), window4g, &base, &p);
         if (e == cudaSuccess) cap = count;
         return e;
     }
     // grow to `count` elements, keeping the first `keep` (device-to-device copy on `st`)
-    cudaError_t grow_keep(size_t count, size_t keep, cudaStream_t st)
+    cudaError_t grow_keep(size_t count, size_t keep, cudaStream_t st, bool window4g = false)
     {
         if (count <= cap && p) return cudaSuccess;
         T *np_ = nullptr;
+        void *nbase = nullptr;
         const size_t want = count + count / 4;          // headroom: query sets vary from call to call
-        cudaError_t e = cudaMalloc(&np_, std::max<size_t>(want, 1) * sizeof(T));
+        cudaError_t e = alloc(want * sizeof(T), window4g, &nbase, &np_);
         if (e != cudaSuccess) return e;
         if (p && keep) {
             e = cudaMemcpyAsync(np_, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st);
             if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-            if (e != cudaSuccess) { cudaFree(np_); return e; }
+            if (e != cudaSuccess) { cudaFree(nbase); return e; }
         }
-        if (p) cudaFree(p);
+        if (base) cudaFree(base);
         p = np_;
+        base = nbase;
         cap = want;
         return cudaSuccess;
     }
     void release()
     {
-        if (p) cudaFree(p);
+        if (base) cudaFree(base);
         p = nullptr;
+        base = nullptr;
         cap = 0;
     }
 };
@@ -726,7 +754,7 @@ static int pack_impl(bgca_engine *e, const uint8_t *ascii, int64_t ascii_bytes, 
     CUDA_TRY(e->d_type.reserve(n));
     CUDA_TRY(e->d_bgc.reserve(n));
     CUDA_TRY(e->d_seq_off.reserve(n));
-    CUDA_TRY(e->d_codes.reserve((size_t)off + 16));
+    CUDA_TRY(e->d_codes.reserve((size_t)off + 16, /*window4g=*/true));
     CUDA_TRY(e->d_err.reserve(1));
     CUDA_TRY(e->d_bgc_start.reserve(e->bgc_start.size()));
     CUDA_TRY(e->d_bgc_doms.reserve(std::max<size_t>(e->bgc_doms.size(), 1)));
@@ -899,7 +927,7 @@ try {
     }
     std::vector<int64_t> off_rel(n_new);
     for (int k = 0; k < n_new; ++k) off_rel[k] = offsets[qord[k]] - offsets[0];
-    CUDA_TRY(e->d_codes.grow_keep((size_t)off + 16, (size_t)e->db_bytes, st));
+    CUDA_TRY(e->d_codes.grow_keep((size_t)off + 16, (size_t)e->db_bytes, st, /*window4g=*/true));
     CUDA_TRY(e->d_offsets_orig.reserve(n_new));
     CUDA_TRY(e->d_order.reserve(n));
     CUDA_TRY(e->d_len.reserve(n));

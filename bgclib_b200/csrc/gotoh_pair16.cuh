@@ -109,6 +109,13 @@ __device__ __forceinline__ uint32_t ldg_token(const uint8_t *p)
     asm("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
+// The packed batch never crosses a 4 GiB boundary (DevBuf::reserve_window in bgca_api.cu sees to
+// it), so the token pointer of the hot loop advances with ONE 32-bit add on its low half instead
+// of a 64-bit add (IADD3 + IADD3.X) on top of a base pointer reloaded from the constant bank.
+__device__ __forceinline__ void advance_lo32(uint64_t &ptr)
+{
+    asm("{\n\t.reg .b32 lo, hi;\n\tmov.b64 {lo, hi}, %0;\n\tadd.u32 lo, lo, 1;\n\tmov.b64 %0, {lo, hi};\n\t}" : "+l"(ptr));
+}
 
 template <int G, int K>
 struct Pair16Cfg {
@@ -187,10 +194,13 @@ gotoh_pair16_kernel(const ScoreParams p)
     // (e,e) / (o,o): immediates under a preset, pre-packed kernel parameters otherwise
     const uint32_t ext2 = PRESET ? Ops::cpack(GapPreset<PRESET>::EXT) : (W32 ? (uint32_t)p.extend : p.ext2);
     const uint32_t open2 = PRESET ? Ops::cpack(GapPreset<PRESET>::OPEN) : (W32 ? (uint32_t)p.open : p.open2);
-    const uint8_t *const idle_ptr = p.codes;            // header of the packed batch: TOK_IDLE bytes
     int *const my_best = sbest + gid * (Cfg::RING * 2);
     // this lane's 16-byte column of the profile, as a 32-bit shared-window address
-    const uint32_t prof_lane = (uint32_t)__cvta_generic_to_shared(prof) + (uint32_t)(G < 8 ? (lane & 7) : t) * 16u;
+    uint32_t prof_lane_v = (uint32_t)__cvta_generic_to_shared(prof) + (uint32_t)(G < 8 ? (lane & 7) : t) * 16u;
+    // opaque: ptxas otherwise rebuilds this address (S2UR, ULEA, shift, mask, add: 7 instructions) in
+    // every step of the hot loop instead of keeping it in a register
+    asm volatile("" : "+r"(prof_lane_v));
+    const uint32_t prof_lane = prof_lane_v;
 
     for (;;) {
         if (tid == 0) s_tile = atomicAdd(p.tile_counter, 1);
@@ -274,7 +284,11 @@ gotoh_pair16_kernel(const ScoreParams p)
         // one LOP3 per value instead of a compare and two selects per step
         uint32_t keep_in = (t == 0 && !from_park) ? 0u : 0xFFFFFFFFu;
         uint32_t top_or = (t == 0 && !from_park) ? open2 : 0u;
-        asm volatile("" : "+r"(keep_in), "+r"(top_or));   // opaque: keeps ptxas from turning them back into selects
+        // through a shuffle with the lane's own index: opaque to ptxas (an empty asm is opaque to the
+        // front end only), which otherwise turns the masks back into a predicate that it rebuilds in
+        // every step, and two selects
+        keep_in = __shfl_sync(FULL, keep_in, lane);
+        top_or = __shfl_sync(FULL, top_or, lane);
 
         // start of a subject whose first residue is c0: state for column 0
         auto begin_subject = [&](uint32_t c0) {
@@ -308,7 +322,7 @@ gotoh_pair16_kernel(const ScoreParams p)
         // offset of the last token fetched.  Every step advances it by one and loads through the
         // updated offset; a lane on idle tokens is put back on the header of idle bytes in the
         // cold path, so the hot loop carries no per-lane increment
-        uint32_t off = 0;                                       // byte offset into p.codes (0 = idle header)
+        uint64_t tokp = (uint64_t)(uintptr_t)p.codes;           // address of the last token fetched (p.codes = idle header)
         uint32_t c = TOK_IDLE, c1 = TOK_IDLE;                   // token of this step / of the next step
 #pragma unroll
         for (int k = 0; k < K; ++k) { Tn[k] = 0; E[k] = 0; }
@@ -316,7 +330,7 @@ gotoh_pair16_kernel(const ScoreParams p)
             const uint8_t *s0 = p.codes + p.seq_off[s_first];
             c = __ldg(s0);
             c1 = __ldg(s0 + 1);
-            off = p.seq_off[s_first] + 1;
+            tokp = (uint64_t)(uintptr_t)(s0 + 1);
             begin_subject(c);
         }
 
@@ -328,8 +342,8 @@ gotoh_pair16_kernel(const ScoreParams p)
         for (int tau = 0; tau < nsteps; ++tau) {
             uint32_t h_in = __shfl_up_sync(FULL, h_out, 1, G);
             uint32_t f_in = __shfl_up_sync(FULL, f_out, 1, G);
-            off += 1;
-            uint32_t c2 = ldg_token(p.codes + off);
+            advance_lo32(tokp);
+            uint32_t c2 = ldg_token(reinterpret_cast<const uint8_t *>(tokp));
             int2 bnd2 = make_int2(0, 0);
             if (MP) {
                 if (park_reader) {              // Ho / F of row row0-1 at this stream position
@@ -339,7 +353,7 @@ gotoh_pair16_kernel(const ScoreParams p)
                 }
             }
             if (LOCAL) {                        // top boundary row: Ho[-1][j] = open, F[-1][j] = 0
-                h_in = (h_in & keep_in) | top_or;
+                asm("lop3.b32 %0, %0, %1, %2, 0xEA;" : "+r"(h_in) : "r"(keep_in), "r"(top_or));   // (h & keep) | top
                 f_in &= keep_in;
             } else if (t == 0 && !from_park) {  // global: Ho[-1][j] walks down the boundary
                 h_in = top_h;
@@ -429,23 +443,23 @@ gotoh_pair16_kernel(const ScoreParams p)
                     const uint8_t *sn = p.codes + p.seq_off[s_first + ord * NGROUPS];
                     c1 = __ldg(sn);
                     c2 = __ldg(sn + 1);
-                    off = p.seq_off[s_first + ord * NGROUPS] + 1;
+                    tokp = (uint64_t)(uintptr_t)(sn + 1);
                     begin_subject(c1);
                 } else {
                     c1 = TOK_IDLE;
                     c2 = TOK_IDLE;
-                    off = 0;
+                    tokp = (uint64_t)(uintptr_t)p.codes;
                     wait = (ord < n_g) ? pad : 0;
                 }
             } else {
                 // ================= cold path: idle token (wind-up of lane t, between two subjects of
                 // an aligned stream, or stream finished) ====
-                off = 0;                        // stay on the header of idle bytes
+                tokp = (uint64_t)(uintptr_t)p.codes;        // stay on the header of idle bytes
                 if (wait > 0 && --wait == 0) {
                     const uint8_t *s0 = p.codes + p.seq_off[s_first + ord * NGROUPS];
                     c1 = __ldg(s0);
                     c2 = __ldg(s0 + 1);
-                    off = p.seq_off[s_first + ord * NGROUPS] + 1;
+                    tokp = (uint64_t)(uintptr_t)(s0 + 1);
                     begin_subject(c1);
                 }
             }
