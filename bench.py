@@ -455,7 +455,7 @@ def main():
         rowbest = torch.randint(0, 2000, (nb, Bb), dtype=torch.int32, device=dev)
         selfsc = torch.randint(1, 3000, (nb,), dtype=torch.int32, device=dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for _ in range(6):
+        for _ in range(11):
             flush.fill_(1)                                     # evict L2 (126 MB) between repetitions
             eng.pack_ascii(ascii_dev, big.offsets, big.type_of_seq, big.bgc_of_seq, Bb)
             k1.append(eng.last_pack_ms())
@@ -465,13 +465,16 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             k5.append(e0.elapsed_time(e1))
-        k1_ms, k5_ms = statistics.median(k1[1:]), statistics.median(k5[1:])
+        # best of 10, the way MEASURED_PEAKS.json took the copy figure these are divided by
+        k1_ms, k5_ms = min(k1[1:]), min(k5[1:])
         k1_bytes = int(big.ascii.nbytes) + int(eng._lib.bgca_packed_bytes(eng._h))
         # rowbest read once, best written once, sim written once (the sim kernel's
         # reads of best / its transpose are re-reads of data just written, not algorithmic bytes)
         k5_bytes = 4 * nb * Bb + 8 * Bb * Bb + 8 * Bb * Bb
         stages = {"workload": f"{nb} synthetic NRPS/PKS domains in {Bb} BGCs (BASELINE config 5), cold L2",
                   "peak_gbs": hbm_peak, "peak_source": peak_src,
+                  "timing": "CUDA events, L2 flushed before every repetition, best of 10 (as the peak was taken); medians in *_ms_median",
+                  "k1_ms_median": statistics.median(k1[1:]), "k5_ms_median": statistics.median(k5[1:]),
                   "k1_pack": {"ms": k1_ms, "algorithmic_bytes": k1_bytes, "gbs": k1_bytes / k1_ms / 1e6,
                               "frac": k1_bytes / k1_ms / 1e6 / hbm_peak},
                   "k5_bgc_reduce": {"ms": k5_ms, "algorithmic_bytes": k5_bytes, "gbs": k5_bytes / k5_ms / 1e6,

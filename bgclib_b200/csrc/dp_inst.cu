@@ -18,7 +18,7 @@
 
 namespace bgca {
 
-constexpr int kMpMaxCtasPerSm = 2;   // the multi-pass kernels' scratch is sized for this many
+constexpr int kMpMaxCtasPerSm = 3;   // the multi-pass kernels' scratch is sized for this many (K <= 18 runs three)
 
 template <int G, int K, int MODE, int PRESET, int MP, int W32 = 0>
 static cudaError_t launch_one(const ScoreParams &p, int n_sm, cudaStream_t st, int *grid_out)

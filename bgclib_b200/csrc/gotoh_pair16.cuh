@@ -161,7 +161,7 @@ template <> struct GapPreset<2> { static constexpr int OPEN = -11, EXT = -1; }; 
 constexpr int NUM_GAP_PRESETS = 3;
 
 template <int G, int K, int MODE, int PRESET, int MP = 0, int W32 = 0>
-__global__ void __launch_bounds__(CTA_THREADS, (MP ? 2 : MODE == BGCA_MODE_LOCAL ? Pair16Cfg<G, K>::MIN_CTAS_LOCAL
+__global__ void __launch_bounds__(CTA_THREADS, (MP ? (K <= 18 && !W32 ? 3 : 2) : MODE == BGCA_MODE_LOCAL ? Pair16Cfg<G, K>::MIN_CTAS_LOCAL
                                                                               : Pair16Cfg<G, K>::MIN_CTAS_GLOBAL))
 gotoh_pair16_kernel(const ScoreParams p)
 {
@@ -270,6 +270,9 @@ gotoh_pair16_kernel(const ScoreParams p)
 #pragma unroll
             for (int off = G; off < 32; off <<= 1) nsteps = max(nsteps, __shfl_xor_sync(FULL, nsteps, off));
         }
+        // the same value in every lane; REDUX leaves it in a uniform register, so the step counter
+        // and its compare run on the uniform datapath instead of the alu pipe
+        nsteps = (int)__reduce_max_sync(FULL, (unsigned)nsteps);
 
         // ---- lane state ------------------------------------------------------------
         // Tn[k] = Ho[i0+k-1][j-1] + (sub(q_{i0+k}, residue j) - open)   diagonal term of the NEXT cell
@@ -287,8 +290,10 @@ gotoh_pair16_kernel(const ScoreParams p)
         // through a shuffle with the lane's own index: opaque to ptxas (an empty asm is opaque to the
         // front end only), which otherwise turns the masks back into a predicate that it rebuilds in
         // every step, and two selects
-        keep_in = __shfl_sync(FULL, keep_in, lane);
-        top_or = __shfl_sync(FULL, top_or, lane);
+        if (G > 1) {
+            keep_in = __shfl_sync(FULL, keep_in, lane);
+            top_or = __shfl_sync(FULL, top_or, lane);
+        }
 
         // start of a subject whose first residue is c0: state for column 0
         auto begin_subject = [&](uint32_t c0) {
@@ -334,14 +339,17 @@ gotoh_pair16_kernel(const ScoreParams p)
             begin_subject(c);
         }
 
-        // multi-pass: the parked row of the previous pass, two steps ahead of its use (lane 0 only)
+        // multi-pass: the parked row of the previous pass, two steps ahead of its use (lane 0 only;
+        // one step ahead leaves the L2 latency exposed: 2 048 residues 7.59 -> 7.26 TCUPS)
         const bool park_reader = from_park && t == 0;
+        const int park_writer = (park && t == G - 1) ? 1 : 0;
         int2 bnd = make_int2(0, 0), bnd1 = make_int2(0, 0);
         if (park_reader) { bnd = __ldcg(mp_line); bnd1 = __ldcg(mp_line + 1); }
 
         for (int tau = 0; tau < nsteps; ++tau) {
-            uint32_t h_in = __shfl_up_sync(FULL, h_out, 1, G);
-            uint32_t f_in = __shfl_up_sync(FULL, f_out, 1, G);
+            // G = 1: the lane holds the whole query, its top boundary is the constant row below
+            uint32_t h_in = (G > 1) ? __shfl_up_sync(FULL, h_out, 1, G) : 0u;
+            uint32_t f_in = (G > 1) ? __shfl_up_sync(FULL, f_out, 1, G) : 0u;
             advance_lo32(tokp);
             uint32_t c2 = ldg_token(reinterpret_cast<const uint8_t *>(tokp));
             int2 bnd2 = make_int2(0, 0);
@@ -353,8 +361,12 @@ gotoh_pair16_kernel(const ScoreParams p)
                 }
             }
             if (LOCAL) {                        // top boundary row: Ho[-1][j] = open, F[-1][j] = 0
-                asm("lop3.b32 %0, %0, %1, %2, 0xEA;" : "+r"(h_in) : "r"(keep_in), "r"(top_or));   // (h & keep) | top
-                f_in &= keep_in;
+                if (G > 1) {
+                    asm("lop3.b32 %0, %0, %1, %2, 0xEA;" : "+r"(h_in) : "r"(keep_in), "r"(top_or));   // (h & keep) | top
+                    f_in &= keep_in;
+                } else {
+                    h_in = open2;
+                }
             } else if (t == 0 && !from_park) {  // global: Ho[-1][j] walks down the boundary
                 h_in = top_h;
                 f_in = Ops::NEG;
@@ -387,8 +399,10 @@ gotoh_pair16_kernel(const ScoreParams p)
                     h_out = up;
                     f_out = F;
                     if (!LOCAL) top_h = Ops::add(top_h, ext2);
-                    if (MP) {                   // bottom row of this pass, by stream position
-                        if (park && t == G - 1) __stcg(mp_line + (tau - (G - 1)), make_int2((int)up, (int)F));
+                    if (MP) {                   // bottom row of this pass, by stream position: one
+                                                // predicated store, no branch around it
+                        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %0, 0;\n\t@q st.global.cg.v2.s32 [%1], {%2, %3};\n\t}"
+                                     :: "r"(park_writer), "l"(mp_line + (tau - (G - 1))), "r"((int)up), "r"((int)F) : "memory");
                     }
                 }
             } else if (c == TOK_BOUNDARY) {

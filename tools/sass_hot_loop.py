@@ -16,10 +16,10 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 LIB = ROOT / "bgclib_b200" / "libbgca.so"
 KERNELS = [
-    ("gotoh_pair16_kernel<16, 28, 0, 1, 0>", "hot kernel of the bench: G=16 lanes x K=28 rows, local, gap preset -12/-1"),
-    ("gotoh_pair16_kernel<16, 28, 1, 1, 0>", "the same, global mode"),
-    ("gotoh_pair16_kernel<1, 20, 0, 1, 0>", "one lane per alignment (20-residue domains)"),
-    ("gotoh_pair16_kernel<32, 24, 0, 1, 1>", "multi-pass whole-warp form (queries > 1024 residues)"),
+    ("gotoh_pair16_kernel<16, 28, 0, 1, 0, 0>", "hot kernel of the bench: G=16 lanes x K=28 rows, local, gap preset -12/-1"),
+    ("gotoh_pair16_kernel<16, 28, 1, 1, 0, 0>", "the same, global mode"),
+    ("gotoh_pair16_kernel<1, 20, 0, 1, 0, 0>", "one lane per alignment (20-residue domains)"),
+    ("gotoh_pair16_kernel<32, 24, 0, 1, 1, 0>", "multi-pass whole-warp form (queries > 1024 residues)"),
     ("gotoh_s32_kernel<0>", "K4: 32-bit fallback, local"),
     ("gotoh_stats2_kernel<0, 14, 0>", "K7: statistics, FP64-compare form, 14 rows per lane, running best in the loop"),
     ("gotoh_stats2_kernel<0, 14, 1>", "K7 with score hints"),
@@ -64,6 +64,53 @@ def hot_stretch(ops):
     return best
 
 
+def step_census(text):
+    """Instructions one step of the streaming loop executes on its hot path: the innermost loop
+    (backward branch) that holds the DP instructions, walked from its head with unconditional
+    forward branches followed (they jump over the cold boundary / idle code) and conditional ones
+    not taken."""
+    ins = []
+    for line in text.splitlines():
+        m = re.match(r"\s+/\*([0-9a-f]{4,5})\*/\s+(.*?);", line)
+        if m:
+            ins.append((int(m.group(1), 16), m.group(2).strip()))
+    pos = {a: i for i, (a, _) in enumerate(ins)}
+    def walk(first, last):
+        hot, i = [], first
+        while i <= last:
+            a, t = ins[i]
+            hot.append(t.split(None, 1)[1].split()[0] if t.startswith("@") else t.split()[0])
+            m = re.match(r"BRA\s+(0x[0-9a-f]+)", t)
+            if m:
+                tgt = int(m.group(1), 16)
+                if tgt > a and tgt in pos:
+                    i = pos[tgt]
+                    continue
+            i += 1
+        return len(hot), sum(1 for o in hot if INTERESTING.match(o))
+
+    # where the unrolled DP step sits: the longest branch-free run with DP instructions
+    def opname(t):
+        return t.split(None, 1)[1].split()[0] if t.startswith("@") else t.split()[0]
+    run0, cur0, stretch = 0, 0, (0, 0, -1)
+    for i, (_, t) in enumerate(ins + [(0, "BRA")]):
+        if opname(t).split(".")[0] in ("BRA", "EXIT", "RET", "BSSY", "BSYNC", "WARPSYNC", "CALL"):
+            n = sum(1 for _, x in ins[cur0:i] if INTERESTING.match(opname(x)))
+            if n > stretch[2]:
+                stretch = (cur0, i - 1, n)
+            cur0 = i + 1
+    best = None
+    for i, (a, t) in enumerate(ins):
+        m = re.search(r"BRA\s+(0x[0-9a-f]+)", t)
+        if not m:
+            continue
+        tgt = int(m.group(1), 16)
+        if tgt < a and tgt in pos and pos[tgt] <= stretch[0] and i >= stretch[1]:
+            if best is None or i - pos[tgt] < best[1] - best[0]:      # the innermost loop around it
+                best = (pos[tgt], i)
+    return walk(*best) if best else None
+
+
 def main():
     print(f"# cuobjdump -sass {LIB.relative_to(ROOT)}  (sm_100a); tools/sass_hot_loop.py")
     for name, what in KERNELS:
@@ -77,6 +124,9 @@ def main():
         c = Counter(o.replace(".reuse", "") for o in hot)
         print(f"\n## {name} — {what}")
         print(f"#  whole function: {len(ops)} instructions; hot stretch (longest branch-free run with DPX/DSETP): {len(hot)}")
+        sc = step_census(text)
+        if sc:
+            print(f"#  one step of the streaming loop, hot path: {sc[0]} instructions, {sc[1]} of them DPX / packed add / DSETP")
         for op, k in c.most_common():
             print(f"{k:6d}  {op}")
 
