@@ -428,6 +428,18 @@ PlanResult make_plan(const int32_t *len, const int32_t *type, const int32_t *rol
     return R;
 }
 
+// Where a buffer of `bytes` bytes may start inside an allocation that begins at `raw` so that it
+// does not cross a 4 GiB address boundary: `raw` itself when [raw, raw + bytes) lies inside one
+// window, else the next boundary (the caller then needs raw + 2 * bytes of room: the boundary is
+// less than `bytes` away).  0: no such start (bytes > 4 GiB).
+uintptr_t window4g_start(uintptr_t raw, size_t bytes)
+{
+    if (bytes == 0) return raw;
+    if (bytes > ((size_t)1 << 32)) return 0;
+    if ((raw >> 32) == ((raw + bytes - 1) >> 32)) return raw;
+    return ((raw >> 32) + 1) << 32;
+}
+
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
@@ -442,18 +454,13 @@ struct DevBuf {
         bytes = std::max<size_t>(bytes, 1);
         cudaError_t e = cudaMalloc(&raw, bytes);
         if (e != cudaSuccess) return e;
-        auto crosses = [&](const void *q) {
-            const uintptr_t a = (uintptr_t)q;
-            return (a >> 32) != ((a + bytes - 1) >> 32);
-        };
         T *use = static_cast<T *>(raw);
-        if (window4g && crosses(raw)) {
-            if (bytes > ((size_t)1 << 32)) { cudaFree(raw); return cudaErrorInvalidValue; }
+        if (window4g && window4g_start((uintptr_t)raw, bytes) != (uintptr_t)raw) {
             cudaFree(raw);
+            if (bytes > ((size_t)1 << 32)) return cudaErrorInvalidValue;
             e = cudaMalloc(&raw, 2 * bytes);
             if (e != cudaSuccess) return e;
-            use = static_cast<T *>(raw);
-            if (crosses(raw)) use = reinterpret_cast<T *>((((uintptr_t)raw >> 32) + 1) << 32);
+            use = reinterpret_cast<T *>(window4g_start((uintptr_t)raw, bytes));
         }
         *base_out = raw;
         *p_out = use;
@@ -572,6 +579,13 @@ extern "C" {
 int bgca_version(void) { return BGCA_VERSION; }
 
 const char *bgca_last_error(void) { return g_last_error.c_str(); }
+
+int bgca_window4g_start(uint64_t raw, uint64_t bytes, uint64_t *start)
+{
+    if (!start) return fail(BGCA_ERR_INVALID, "bgca_window4g_start: start is NULL");
+    *start = (uint64_t)window4g_start((uintptr_t)raw, (size_t)bytes);
+    return *start || !bytes ? BGCA_OK : fail(BGCA_ERR_INVALID, "bgca_window4g_start: more than 4 GiB");
+}
 
 int bgca_create(int device, bgca_engine **out)
 try {

@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = (
     "bgca_pack", "bgca_pack_spans", "bgca_pack_append", "bgca_packed_bytes", "bgca_get_packed", "bgca_plan", "bgca_plan_host",
     "bgca_score", "bgca_score_pairs32", "bgca_pair_stats", "bgca_pair_stats_hinted", "bgca_select_pairs",
     "bgca_pair_stats_selected", "bgca_reduce_bgc", "bgca_score_all_host",
-    "bgca_last_launches", "bgca_last_dp_ms", "bgca_last_pack_ms", "bgca_dpx_probe",
+    "bgca_last_launches", "bgca_last_dp_ms", "bgca_last_pack_ms", "bgca_dpx_probe", "bgca_window4g_start",
 )
 
 
@@ -93,6 +93,7 @@ def load_library():
     lib.bgca_last_dp_ms.argtypes = [vp, P(ctypes.c_float)]
     lib.bgca_last_pack_ms.argtypes = [vp, P(ctypes.c_float)]
     lib.bgca_dpx_probe.argtypes = [ctypes.c_int, P(ctypes.c_double), i32]
+    lib.bgca_window4g_start.argtypes = [ctypes.c_uint64, ctypes.c_uint64, P(ctypes.c_uint64)]
     for name in EXPORTED_SYMBOLS:
         getattr(lib, name)   # AttributeError here = header and library out of step
     _lib = lib

@@ -235,6 +235,14 @@ int bgca_last_dp_ms(bgca_engine *e, float *ms);
 /* Device time of the K1 kernel of the last bgca_pack() in ms (CUDA events on its stream). */
 int bgca_last_pack_ms(bgca_engine *e, float *ms);
 
+/* The placement rule of the packed batch, exposed for the host tests: the DP kernels advance
+ * their token pointer with a 32-bit add on its low half, so the batch must lie inside one 4 GiB
+ * address window.  Given an allocation that starts at `raw`, *start = where a buffer of `bytes`
+ * bytes may begin: `raw` when [raw, raw + bytes) crosses no 4 GiB boundary, else the next
+ * boundary (less than `bytes` away, so an allocation of 2 * bytes always has room).
+ * BGCA_ERR_INVALID for more than 4 GiB (cannot happen: packed offsets are 32-bit). */
+int bgca_window4g_start(uint64_t raw, uint64_t bytes, uint64_t *start);
+
 /* Calibration microbenchmark: issue rate of the DPX/ALU ops
  * the DP kernels are made of.  Fills out[0..n) with lane-ops per clock per SM
  * for: 0 VIADDMNMX.S16x2, 1 VIMNMX3.S16x2, 2 VIMNMX.S16x2, 3 VIADD.16x2

@@ -29,6 +29,28 @@ def test_library_exports_every_declared_symbol():
     assert lib.bgca_version() == 105
 
 
+def test_packed_batch_stays_inside_one_4gib_window():
+    """The DP kernels add to the low half of their token pointer only (gotoh_pair16.cuh,
+    advance_lo32): whatever cudaMalloc returns, the packed batch must start where it crosses no
+    4 GiB boundary, and that start must lie inside an allocation of twice its size."""
+    lib = eng.load_library()
+    G = 1 << 32
+    rng = np.random.default_rng(7)
+    cases = [(0x7F0000000, 1), (0x7FFFFFFFF, 1), (0x7FFFFFFFF, 2), (0x7FFFF0000, 0x10000), (0x7FFFF0000, 0x10001),
+             (5 * G, G), (5 * G + 512, G), (5 * G - 512, 42 << 20), (3 * G - 1, G)]
+    cases += [(int(rng.integers(1, 1 << 46)) & ~0xFF, int(rng.integers(1, 3 << 30))) for _ in range(2000)]
+    for raw, nbytes in cases:
+        out = ctypes.c_uint64()
+        assert lib.bgca_window4g_start(raw, nbytes, ctypes.byref(out)) == 0
+        start = out.value
+        assert start >> 32 == (start + nbytes - 1) >> 32, (raw, nbytes)      # one window
+        assert raw <= start and start + nbytes <= raw + 2 * nbytes, (raw, nbytes)   # inside the 2x allocation
+        if raw >> 32 == (raw + nbytes - 1) >> 32:
+            assert start == raw                                               # nothing to do: nothing moved
+    out = ctypes.c_uint64()
+    assert lib.bgca_window4g_start(G, G + 1, ctypes.byref(out)) == eng.BGCA_ERR_INVALID
+
+
 def test_no_device_fails_loudly():
     import torch
     if torch.cuda.is_available():
