@@ -109,8 +109,8 @@ __device__ __forceinline__ uint32_t ldg_token(const uint8_t *p)
     asm("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
-// The packed batch never crosses a 4 GiB boundary (DevBuf::reserve_window in bgca_api.cu sees to
-// it), so the token pointer of the hot loop advances with ONE 32-bit add on its low half instead
+// The packed batch never crosses a 4 GiB boundary (DevBuf::alloc / window4g_start in bgca_api.cu
+// see to it), so the token pointer of the hot loop advances with ONE 32-bit add on its low half instead
 // of a 64-bit add (IADD3 + IADD3.X) on top of a base pointer reloaded from the constant bank.
 __device__ __forceinline__ void advance_lo32(uint64_t &ptr)
 {
@@ -324,9 +324,9 @@ gotoh_pair16_kernel(const ScoreParams p)
 
         int ord = 0;                                            // subjects this lane has finished
         int wait = (n_g > 0) ? t : 0;                           // idle steps before this lane starts
-        // offset of the last token fetched.  Every step advances it by one and loads through the
-        // updated offset; a lane on idle tokens is put back on the header of idle bytes in the
-        // cold path, so the hot loop carries no per-lane increment
+        // address of the last token fetched.  Every step advances it by one (low half only, see
+        // advance_lo32) and loads through it; a lane on idle tokens is put back on the header of idle
+        // bytes in the cold path, so the hot loop carries no test of where the pointer stands
         uint64_t tokp = (uint64_t)(uintptr_t)p.codes;           // address of the last token fetched (p.codes = idle header)
         uint32_t c = TOK_IDLE, c1 = TOK_IDLE;                   // token of this step / of the next step
 #pragma unroll

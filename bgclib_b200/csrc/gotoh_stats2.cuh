@@ -153,6 +153,9 @@ gotoh_stats2_kernel(const Stats2Params p)
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) nsteps += __shfl_xor_sync(FULL, nsteps, off);
         nsteps = (n_w > 0) ? nsteps + 31 : 0;
+        // the same value in every lane; out of a REDUX it sits in a uniform register and the step
+        // counter leaves the alu pipe (724 -> 766 GCUPS local, 792 -> 823 with hints, 823 -> 849 global)
+        nsteps = (int)__reduce_max_sync(FULL, (unsigned)nsteps);
 
         // ---- lane state ---------------------------------------------------------------------
         // Tn = H[i0+k-1][j-1] + delta(q_{i0+k}, residue j): the diagonal term of the NEXT column
