@@ -80,6 +80,11 @@ struct Stats2Cfg {
     static constexpr int SLOT_BYTES = ST2_WARPS * 32 * 16;           // per warp a ring of 32 best slots
     static constexpr int SMEM_BYTES = PROF_BYTES + SLOT_BYTES + LPAD + NSYM * NSYM + 16;
     static constexpr int MIN_CTAS = (KS <= 8) ? 6 : (KS <= 12) ? 5 : (KS <= 16) ? 4 : (KS <= 20) ? 3 : 2;
+    // The kernels with score hints and the global ones carry a few more live values: one CTA per SM
+    // less where the tighter register budget made ptxas spill inside the step (measured with hints /
+    // global, GCUPS: 240-residue domains 706 / 746 -> 795 / 818, 370: 762 / 810 -> 787 / 831,
+    // 500: 713 / 782 -> 730 / 797; the 20-row class is better off where it was).
+    static constexpr int MIN_CTAS_TIGHT = (KS <= 8) ? 5 : (KS <= 12) ? 4 : (KS <= 20) ? 3 : 2;
 };
 
 // A DP value lives in a double (the 64-bit word described above, a positive finite number): the
@@ -91,7 +96,7 @@ __device__ __forceinline__ uint32_t st2_hi(st2_t v) { return (uint32_t)__double2
 __device__ __forceinline__ uint32_t st2_lo(st2_t v) { return (uint32_t)__double2loint(v); }
 
 template <int MODE, int KS, int HINT = 0>
-__global__ void __launch_bounds__(ST2_THREADS, Stats2Cfg<KS>::MIN_CTAS)
+__global__ void __launch_bounds__(ST2_THREADS, ((HINT || MODE == BGCA_MODE_GLOBAL) ? Stats2Cfg<KS>::MIN_CTAS_TIGHT : Stats2Cfg<KS>::MIN_CTAS))
 gotoh_stats2_kernel(const Stats2Params p)
 {
     using Cfg = Stats2Cfg<KS>;

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=200_000)
     ap.add_argument("--mode", default="local")
     ap.add_argument("--n-seqs", type=int, default=10_000)
+    ap.add_argument("--length", type=int, default=0, help="mean domain length (default: config 3, ~420)")
     ap.add_argument("--hinted", action="store_true", help="give the kernels the pairs' scores (bgca_pair_stats_hinted)")
     ap.add_argument("--above", type=int, default=None,
                     help="instead of a random list: score an --n-seqs collection all-vs-all and run the statistics "
@@ -30,7 +31,12 @@ def main():
     import torch
     import bgclib_b200
     from bgclib_b200 import synth
-    col = synth.ks_like(args.n_seqs)
+    if args.length:        # another length class than config 3's (the kernels are instantiated per rows-per-lane class)
+        sd = max(1.0, 0.035 * args.length)
+        col = synth.ks_like(args.n_seqs, seed=args.length, mean=args.length, sd=sd,
+                            lo=max(1, int(args.length - 4 * sd)), hi=int(args.length + 4 * sd))
+    else:
+        col = synth.ks_like(args.n_seqs)
     eng = bgclib_b200.get_engine(0)
     eng.set_scoring("BLOSUM62", -12, -1, args.mode)
     eng.pack_ascii(col.ascii, col.offsets)
