@@ -84,7 +84,9 @@ struct Stats2Cfg {
     // less where the tighter register budget made ptxas spill inside the step (measured with hints /
     // global, GCUPS: 240-residue domains 706 / 746 -> 795 / 818, 370: 762 / 810 -> 787 / 831,
     // 500: 713 / 782 -> 730 / 797; the 20-row class is better off where it was).
-    static constexpr int MIN_CTAS_TIGHT = (KS <= 8) ? 5 : (KS <= 12) ? 4 : (KS <= 20) ? 3 : 2;
+    // The 14-row class with hints keeps four (12 bytes of spill; at three: 823 -> 767 GCUPS).
+    static constexpr int MIN_CTAS_HINT = (KS <= 8) ? 5 : (KS <= 14) ? 4 : (KS <= 20) ? 3 : 2;
+    static constexpr int MIN_CTAS_GLOBAL = (KS <= 8) ? 5 : (KS <= 12) ? 4 : (KS <= 20) ? 3 : 2;
 };
 
 // A DP value lives in a double (the 64-bit word described above, a positive finite number): the
@@ -96,7 +98,7 @@ __device__ __forceinline__ uint32_t st2_hi(st2_t v) { return (uint32_t)__double2
 __device__ __forceinline__ uint32_t st2_lo(st2_t v) { return (uint32_t)__double2loint(v); }
 
 template <int MODE, int KS, int HINT = 0>
-__global__ void __launch_bounds__(ST2_THREADS, ((HINT || MODE == BGCA_MODE_GLOBAL) ? Stats2Cfg<KS>::MIN_CTAS_TIGHT : Stats2Cfg<KS>::MIN_CTAS))
+__global__ void __launch_bounds__(ST2_THREADS, (HINT ? Stats2Cfg<KS>::MIN_CTAS_HINT : MODE == BGCA_MODE_GLOBAL ? Stats2Cfg<KS>::MIN_CTAS_GLOBAL : Stats2Cfg<KS>::MIN_CTAS))
 gotoh_stats2_kernel(const Stats2Params p)
 {
     using Cfg = Stats2Cfg<KS>;
