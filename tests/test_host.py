@@ -476,3 +476,29 @@ def test_hand_built_batches_need_unique_type_keys_and_bgc_ids():
                 DomainBatch(["ACD", "ACE"], [], ["b0", "b0"], np.array([0, 1], np.int32), ["KS", "AT"], np.array([0, 1], np.int32))):
         with pytest.raises(ValueError, match="unique"):
             _as_batch(bad, "domain", True, None, None)
+
+
+def test_bench_reference_arm_line_contract():
+    """`bench.py --impl reference` (the oracle port on the host cores — the one place besides the
+    tests where bench.py may execute oracle/): one JSON line with the keys the driver divides by,
+    the same `config` keys and units as the GPU arm's line, no GPU needed."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--n-seqs", "400", "--cpu-seconds", "0.5"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "GCUPS" and line["unit"] == "GCUPS"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["n_gpus"] == 1
+    assert line["e2e"] == {"value": line["value"], "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sequences" in cb["sample"]
+    assert set(line["config"]) == {"workload", "mode", "matrix", "open", "extend"}
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_for_test", ROOT / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert set(bench.bench_config("x")) == set(line["config"])     # the GPU arm prints the same keys
