@@ -50,6 +50,7 @@
 //   best = max3(best, H_even, H_odd)     VIMNMX3.S16x2          alu pipe, every 2nd cell (local)
 // = 5.5 issue slots per 2 cells of which 3.5 on the alu pipe (local); 5 / 3 (global).
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace bgca {
@@ -341,8 +342,13 @@ gotoh_pair16_kernel(const ScoreParams p)
 
         // multi-pass: the parked row of the previous pass, two steps ahead of its use (lane 0 only;
         // one step ahead leaves the L2 latency exposed: 2 048 residues 7.59 -> 7.26 TCUPS)
-        const bool park_reader = from_park && t == 0;
-        const int park_writer = (park && t == G - 1) ? 1 : 0;
+        // The sweep is instantiated per role of the pass — RD: it reads the row the previous pass
+        // parked, WR: it parks its own bottom row — so that a first pass issues none of the reader's
+        // instructions and a last pass none of the writer's (single-pass kernels: neither).
+        auto sweep = [&](auto rd_tag, auto wr_tag) {
+        constexpr bool RD = MP && decltype(rd_tag)::value, WR = MP && decltype(wr_tag)::value;
+        const bool park_reader = RD && t == 0;
+        const int park_writer = (WR && t == G - 1) ? 1 : 0;
         int2 bnd = make_int2(0, 0), bnd1 = make_int2(0, 0);
         if (park_reader) { bnd = __ldcg(mp_line); bnd1 = __ldcg(mp_line + 1); }
 
@@ -353,7 +359,7 @@ gotoh_pair16_kernel(const ScoreParams p)
             advance_lo32(tokp);
             uint32_t c2 = ldg_token(reinterpret_cast<const uint8_t *>(tokp));
             int2 bnd2 = make_int2(0, 0);
-            if (MP) {
+            if (RD) {
                 if (park_reader) {              // Ho / F of row row0-1 at this stream position
                     bnd2 = __ldcg(mp_line + tau + 2);
                     h_in = (uint32_t)bnd.x;
@@ -399,7 +405,7 @@ gotoh_pair16_kernel(const ScoreParams p)
                     h_out = up;
                     f_out = F;
                     if (!LOCAL) top_h = Ops::add(top_h, ext2);
-                    if (MP) {                   // bottom row of this pass, by stream position: one
+                    if (WR) {                   // bottom row of this pass, by stream position: one
                                                 // predicated store, no branch around it
                         asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %0, 0;\n\t@q st.global.cg.v2.s32 [%1], {%2, %3};\n\t}"
                                      :: "r"(park_writer), "l"(mp_line + (tau - (G - 1))), "r"((int)up), "r"((int)F) : "memory");
@@ -479,8 +485,14 @@ gotoh_pair16_kernel(const ScoreParams p)
             }
             c = c1;
             c1 = c2;
-            if (MP) { bnd = bnd1; bnd1 = bnd2; }
+            if (RD) { bnd = bnd1; bnd1 = bnd2; }
         }
+        };  // sweep
+        if (!MP) sweep(std::false_type{}, std::false_type{});
+        else if (from_park && park) sweep(std::true_type{}, std::true_type{});
+        else if (from_park) sweep(std::true_type{}, std::false_type{});
+        else if (park) sweep(std::false_type{}, std::true_type{});
+        else sweep(std::false_type{}, std::false_type{});
       }   // pass
     }
 }
